@@ -1,0 +1,658 @@
+// api.cu -- the extern "C" surface of libfpa_b200.so (declared in include/fpa_b200.h).
+//
+// Everything in this file is plumbing around the kernels of yaman4.cu / frontend.cu / nwave.cu /
+// linear.cu / probe.cu: argument checks, device selection, a grow-only device workspace for the
+// host-pointer entry points, H2D / D2H staging and error text.  No arithmetic of the hot path
+// lives here and nothing here can run the path on the CPU: without a CUDA device every compute
+// entry point returns FPA_ERR_NO_DEVICE.
+#include "fpa_common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+
+#include <map>
+#include <tuple>
+
+namespace fpa {
+
+// launchers implemented next to their kernels
+int yaman4_launch(const fpa_yaman4_desc* d, cudaStream_t st);
+int yaman4_rhs_launch(int64_t B, const double* z, const double* A, const double* gamma,
+                      const double* alpha, const double* dbeta, double* dA, cudaStream_t st);
+int plan_launch(const fpa_plan_desc* d, double* dbeta_masked, cudaStream_t st);
+int sweep_consts_launch(double gamma, double alpha, const double* A0, double* consts, cudaStream_t st);
+int sweep_gain_launch(int64_t B, const double* Pmax, const int32_t* valid, const int32_t* status,
+                      double p_signal, int check_nan, double* gain_lin, cudaStream_t st);
+int linear_launch(int64_t B, int dim, const double* y0, const double* lam, double z0, double z_max,
+                  int64_t n_steps, int64_t save_every, const double* z_grid, uint32_t flags,
+                  double* y_trace, double* y_end, int32_t* bad_scratch, int32_t* status,
+                  cudaStream_t st);
+int nwave_launch(const fpa_nwave_desc* d, cudaStream_t st);
+int probe_run(int device, int iters, double* tflops, double* ms_out);
+
+// ----------------------------------------------------------------- error text (per host thread)
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    // leave the runtime's sticky "last error" clean for the next call
+    cudaGetLastError();
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return FPA_ERR_NO_DEVICE;
+    return FPA_ERR_CUDA;
+}
+
+int use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device is visible: libfpa_b200 has no CPU path");
+        return FPA_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device %d out of range [0, %d)", device, n);
+        return FPA_ERR_INVALID;
+    }
+    FPA_CUDA(cudaSetDevice(device));
+    return FPA_OK;
+}
+
+// ----------------------------------------------------------------- grow-only workspace
+struct Slab {
+    void*  ptr = nullptr;
+    size_t cap = 0;
+};
+static thread_local std::map<std::pair<int, int>, Slab> g_slabs;
+
+int workspace(int device, int slot, size_t bytes, void** out) {
+    Slab& s = g_slabs[std::make_pair(device, slot)];
+    if (bytes > s.cap) {
+        if (s.ptr) {
+            FPA_CUDA(cudaDeviceSynchronize());
+            FPA_CUDA(cudaFree(s.ptr));
+            s.ptr = nullptr;
+            s.cap = 0;
+        }
+        // round up so that slowly growing batches do not reallocate every call
+        size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        FPA_CUDA(cudaMalloc(&s.ptr, want));
+        s.cap = want;
+    }
+    *out = s.ptr;
+    return FPA_OK;
+}
+
+// bump allocator over one workspace slab (256-byte aligned pieces)
+struct Carver {
+    char*  base = nullptr;
+    size_t off  = 0;
+    template <class T>
+    T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + off);
+        off += (count * sizeof(T) + 255) & ~(size_t)255;
+        return p;
+    }
+    static size_t need(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+};
+
+static int up(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return FPA_OK;
+    FPA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return FPA_OK;
+}
+static int down(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0 || dst == nullptr) return FPA_OK;
+    FPA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    return FPA_OK;
+}
+
+#define FPA_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != FPA_OK) return rc__; \
+    } while (0)
+
+// One non-blocking stream per (host thread, device) for the host-pointer entry points.
+static thread_local std::map<int, cudaStream_t> g_streams;
+static int host_stream(int device, cudaStream_t* st) {
+    auto it = g_streams.find(device);
+    if (it == g_streams.end()) {
+        cudaStream_t s;
+        FPA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        it = g_streams.emplace(device, s).first;
+    }
+    *st = it->second;
+    return FPA_OK;
+}
+
+// ----------------------------------------------------------------- sweep (device pointers)
+struct SweepScratch {
+    double*  consts;
+    double*  dbeta_run;
+    double*  Pmax;
+    int32_t* status;
+    int32_t* valid;
+    double*  dbeta_report;
+};
+
+static size_t sweep_scratch_need(int64_t B) {
+    const size_t b = (size_t)(B > 0 ? B : 0);
+    return Carver::need(16 * sizeof(double)) + Carver::need(b * sizeof(double)) +
+           Carver::need(4 * b * sizeof(double)) + 2 * Carver::need(b * sizeof(int32_t)) +
+           Carver::need(b * sizeof(double));
+}
+
+static int sweep_dev(const fpa_sweep_desc* d, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
+    FPA_REQUIRE(d != nullptr, "sweep descriptor is NULL");
+    const fpa_plan_desc& pl = d->plan;
+    FPA_REQUIRE(pl.n1 >= 0 && pl.n3 >= 0, "grid sizes must be >= 0");
+    const int64_t B = pl.n1 * pl.n3;
+    FPA_REQUIRE(d->gain_lin != nullptr || B == 0, "gain_lin must be set");
+    FPA_REQUIRE(d->length_scale == 1.0 || d->length_scale == 1000.0, "length_scale must be 1 or 1000");
+    FPA_REQUIRE(d->z_max > 0.0, "z_max must be positive");
+    FPA_REQUIRE(d->dz > 0.0, "dz must be positive");
+    FPA_REQUIRE(d->save_every >= 1, "save_every must be a positive integer");
+    FPA_REQUIRE(d->p_signal > 0.0, "p_in[2] (signal seed power) must be > 0 to define gain");
+    FPA_REQUIRE(scratch_bytes >= (int64_t)sweep_scratch_need(B), "scratch too small: need %lld bytes",
+                (long long)sweep_scratch_need(B));
+    if (B == 0) return FPA_OK;
+
+    Carver cv;
+    cv.base = static_cast<char*>(scratch);
+    SweepScratch s;
+    s.consts       = cv.take<double>(16);
+    s.dbeta_run    = cv.take<double>(B);
+    s.Pmax         = cv.take<double>(4 * B);
+    s.status       = cv.take<int32_t>(B);
+    s.valid        = cv.take<int32_t>(B);
+    s.dbeta_report = cv.take<double>(B);
+
+    const double sc = d->length_scale;
+    double*  Pmax   = d->Pmax ? d->Pmax : s.Pmax;
+    int32_t* status = d->status ? d->status : s.status;
+    int32_t* valid  = pl.valid ? pl.valid : s.valid;
+    double*  report = pl.dbeta ? pl.dbeta : s.dbeta_report;
+
+    // (1) reported dbeta: the dispersion exactly as the caller gave it (scan_mismtach.py:700-706)
+    fpa_plan_desc rep = pl;
+    rep.dbeta = report;
+    rep.valid = valid;
+    FPA_TRY(plan_launch(&rep, nullptr, st));
+    // (2) dbeta used by the integration: every beta_n (or the PROVIDED constant) divided by the
+    //     length scale first (simulation.py:126-175), then the same provider.
+    const double* dbeta_run = report;
+    if (sc != 1.0) {
+        fpa_plan_desc run = pl;
+        for (int n = 0; n <= FPA_MAX_TAYLOR_ORDER; ++n) run.beta[n] = pl.beta[n] / sc;
+        run.provided = pl.provided / sc;
+        run.omega = nullptr;
+        run.dbeta = s.dbeta_run;
+        run.valid = nullptr;
+        FPA_TRY(plan_launch(&run, nullptr, st));
+        dbeta_run = s.dbeta_run;
+    }
+    // (3) per-sweep constants -> device (gamma/scale, alpha/scale, A0)
+    FPA_TRY(sweep_consts_launch(d->gamma / sc, d->alpha / sc, d->A0, s.consts, st));
+    // (4) the fused integrator; invalid points carry dbeta = NaN and leave at once
+    fpa_yaman4_desc y;
+    memset(&y, 0, sizeof(y));
+    y.n_points     = B;
+    y.dbeta        = dbeta_run;
+    y.gamma        = s.consts;
+    y.gamma_stride = 0;
+    y.alpha        = s.consts + 1;
+    y.alpha_stride = 0;
+    y.A0           = s.consts + 2;
+    y.A0_stride    = 0;
+    y.z0           = 0.0;
+    y.z_max        = d->z_max * sc;
+    y.n_steps      = fpa_interval_steps(d->z_max * sc, d->dz * sc);
+    FPA_REQUIRE(y.n_steps >= 1, "z_max/dz rounds to zero steps");
+    y.save_every   = d->save_every;
+    y.flags        = FPA_OUT_PMAX | (d->flags & (FPA_CHECK_NAN | FPA_PHASE_EXACT)) |
+                     (d->A_end ? FPA_OUT_END : 0u);
+    y.Pmax         = Pmax;
+    y.A_end        = d->A_end;
+    y.status       = status;
+    FPA_TRY(yaman4_launch(&y, st));
+    // (5) gain metric (scan_mismtach.py:723-734)
+    FPA_TRY(sweep_gain_launch(B, Pmax, valid, status, d->p_signal, (d->flags & FPA_CHECK_NAN) ? 1 : 0,
+                              d->gain_lin, st));
+    return FPA_OK;
+}
+
+}  // namespace fpa
+
+using namespace fpa;
+
+// =================================================================== extern "C"
+extern "C" {
+
+const char* fpa_last_error(void) { return g_err; }
+const char* fpa_version(void) { return "fpa_b200 0.1 (sm_100a)"; }
+
+int fpa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int fpa_device_info(int device, int* sm_count, int* clock_khz, char* name, int name_cap) {
+    FPA_TRY(use_device(device));
+    cudaDeviceProp prop;
+    FPA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (clock_khz) {
+        int khz = 0;
+        FPA_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+        *clock_khz = khz;
+    }
+    if (name && name_cap > 0) {
+        strncpy(name, prop.name, (size_t)name_cap - 1);
+        name[name_cap - 1] = '\0';
+    }
+    return FPA_OK;
+}
+
+int64_t fpa_n_saved(int64_t n_steps, int64_t save_every) {
+    if (n_steps < 0 || save_every < 1) return -1;
+    return n_steps / save_every + 1;
+}
+
+int64_t fpa_interval_steps(double z_max, double dz) {
+    // Python's round() on a float is round-half-to-even == nearbyint in the default FP mode
+    const double q = z_max / dz;
+    if (!(q == q) || fabs(q) > 9.0e15) return -1;
+    return (int64_t)nearbyint(q);
+}
+
+double fpa_yaman4_flops_per_step(void) { return 568.0; }
+
+// ------------------------------------------------------------------ 4-wave integrator
+int fpa_yaman4_rk4_batch_dev(const fpa_yaman4_desc* d, void* stream) {
+    int n = fpa_device_count();
+    if (n <= 0) {
+        set_error("no CUDA device is visible: libfpa_b200 has no CPU path");
+        return FPA_ERR_NO_DEVICE;
+    }
+    return yaman4_launch(d, static_cast<cudaStream_t>(stream));
+}
+
+int fpa_yaman4_rk4_batch_host(const fpa_yaman4_desc* d, int device) {
+    FPA_REQUIRE(d != nullptr, "descriptor is NULL");
+    FPA_REQUIRE(d->n_points >= 0, "n_points must be >= 0");
+    FPA_REQUIRE(d->n_steps >= 1, "n_steps must be >= 1");
+    FPA_REQUIRE(d->save_every >= 1, "save_every must be a positive integer");
+    FPA_REQUIRE(d->dbeta && d->gamma && d->alpha && d->A0, "dbeta/gamma/alpha/A0 must be set");
+    FPA_REQUIRE((d->gamma_stride | 1) == 1 && (d->alpha_stride | 1) == 1 && (d->A0_stride | 1) == 1,
+                "strides must be 0 (broadcast) or 1 (per point)");
+    FPA_TRY(use_device(device));
+    const size_t B = (size_t)d->n_points;
+    if (B == 0) return FPA_OK;
+    const size_t ns     = (size_t)fpa_n_saved(d->n_steps, d->save_every);
+    const size_t n_g    = d->gamma_stride ? B : 1, n_a = d->alpha_stride ? B : 1;
+    const size_t n_A0   = (d->A0_stride ? B : 1) * 8;
+    const size_t n_grid = d->z_grid ? (size_t)d->n_steps + 1 : 0;
+    const bool   trace = (d->flags & FPA_OUT_TRACE) != 0, endo = (d->flags & FPA_OUT_END) != 0;
+    const bool   pmax = (d->flags & FPA_OUT_PMAX) != 0;
+    const size_t n_tr = trace ? B * ns * 8 : 0;
+
+    size_t need = Carver::need(B * 8) + Carver::need(n_g * 8) + Carver::need(n_a * 8) +
+                  Carver::need(n_A0 * 8) + Carver::need(n_grid * 8) + Carver::need(n_tr * 8) +
+                  Carver::need(B * 64) + Carver::need(B * 32) + Carver::need(B * 4);
+    void* ws = nullptr;
+    FPA_TRY(workspace(device, 0, need, &ws));
+    cudaStream_t st;
+    FPA_TRY(host_stream(device, &st));
+    Carver cv;
+    cv.base = static_cast<char*>(ws);
+    double*  dbeta = cv.take<double>(B);
+    double*  gam   = cv.take<double>(n_g);
+    double*  alp   = cv.take<double>(n_a);
+    double*  A0    = cv.take<double>(n_A0);
+    double*  grid  = cv.take<double>(n_grid);
+    double*  tr    = cv.take<double>(n_tr);
+    double*  Aend  = cv.take<double>(B * 8);
+    double*  Pm    = cv.take<double>(B * 4);
+    int32_t* stat  = cv.take<int32_t>(B);
+
+    FPA_TRY(up(dbeta, d->dbeta, B * 8, st));
+    FPA_TRY(up(gam, d->gamma, n_g * 8, st));
+    FPA_TRY(up(alp, d->alpha, n_a * 8, st));
+    FPA_TRY(up(A0, d->A0, n_A0 * 8, st));
+    FPA_TRY(up(grid, d->z_grid, n_grid * 8, st));
+
+    fpa_yaman4_desc dd = *d;
+    dd.dbeta   = dbeta;
+    dd.gamma   = gam;
+    dd.alpha   = alp;
+    dd.A0      = A0;
+    dd.z_grid  = d->z_grid ? grid : nullptr;
+    dd.A_trace = trace ? tr : nullptr;
+    dd.A_end   = endo ? Aend : nullptr;
+    dd.Pmax    = pmax ? Pm : nullptr;
+    dd.status  = stat;
+    FPA_REQUIRE(!trace || d->A_trace, "FPA_OUT_TRACE needs A_trace");
+    FPA_REQUIRE(!pmax || d->Pmax, "FPA_OUT_PMAX needs Pmax");
+    FPA_REQUIRE(!endo || d->A_end, "FPA_OUT_END needs A_end");
+    FPA_TRY(yaman4_launch(&dd, st));
+
+    if (trace) FPA_TRY(down(d->A_trace, tr, n_tr * 8, st));
+    if (endo) FPA_TRY(down(d->A_end, Aend, B * 64, st));
+    if (pmax) FPA_TRY(down(d->Pmax, Pm, B * 32, st));
+    FPA_TRY(down(d->status, stat, B * 4, st));
+    FPA_CUDA(cudaStreamSynchronize(st));
+    return FPA_OK;
+}
+
+int fpa_yaman4_rhs_host(int64_t B, const double* z, const double* A, const double* gamma,
+                        const double* alpha, const double* dbeta, double* dA, int device) {
+    FPA_REQUIRE(B >= 0, "B must be >= 0");
+    FPA_REQUIRE(B == 0 || (z && A && gamma && alpha && dbeta && dA), "NULL argument");
+    FPA_TRY(use_device(device));
+    if (B == 0) return FPA_OK;
+    const size_t b = (size_t)B;
+    void* ws = nullptr;
+    FPA_TRY(workspace(device, 1, 4 * Carver::need(b * 8) + 2 * Carver::need(b * 64), &ws));
+    cudaStream_t st;
+    FPA_TRY(host_stream(device, &st));
+    Carver cv;
+    cv.base = static_cast<char*>(ws);
+    double* dz = cv.take<double>(b);
+    double* dg = cv.take<double>(b);
+    double* da = cv.take<double>(b);
+    double* db = cv.take<double>(b);
+    double* dA_in = cv.take<double>(b * 8);
+    double* dA_out = cv.take<double>(b * 8);
+    FPA_TRY(up(dz, z, b * 8, st));
+    FPA_TRY(up(dg, gamma, b * 8, st));
+    FPA_TRY(up(da, alpha, b * 8, st));
+    FPA_TRY(up(db, dbeta, b * 8, st));
+    FPA_TRY(up(dA_in, A, b * 64, st));
+    FPA_TRY(yaman4_rhs_launch(B, dz, dA_in, dg, da, db, dA_out, st));
+    FPA_TRY(down(dA, dA_out, b * 64, st));
+    FPA_CUDA(cudaStreamSynchronize(st));
+    return FPA_OK;
+}
+
+// ------------------------------------------------------------------ Delta-beta table
+int fpa_dbeta_table_dev(const fpa_plan_desc* d, void* stream) {
+    if (fpa_device_count() <= 0) {
+        set_error("no CUDA device is visible: libfpa_b200 has no CPU path");
+        return FPA_ERR_NO_DEVICE;
+    }
+    return plan_launch(d, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int fpa_dbeta_table_host(const fpa_plan_desc* d, int device) {
+    FPA_REQUIRE(d != nullptr, "plan descriptor is NULL");
+    FPA_REQUIRE(d->n1 >= 0 && d->n3 >= 0, "grid sizes must be >= 0");
+    FPA_REQUIRE(d->lambda1 && d->lambda2 && d->lambda3, "wavelength axes must be set");
+    FPA_REQUIRE(d->dbeta != nullptr, "dbeta output must be set");
+    FPA_TRY(use_device(device));
+    const size_t n1 = (size_t)d->n1, n3 = (size_t)d->n3, B = n1 * n3;
+    if (B == 0) return FPA_OK;
+    const size_t n2 = d->lambda2_stride ? n1 : 1;
+    void*        ws = nullptr;
+    FPA_TRY(workspace(device, 2,
+                      Carver::need(n1 * 8) + Carver::need(n2 * 8) + Carver::need(n3 * 8) +
+                          Carver::need(B * 32) + Carver::need(B * 8) + Carver::need(B * 4),
+                      &ws));
+    cudaStream_t st;
+    FPA_TRY(host_stream(device, &st));
+    Carver cv;
+    cv.base = static_cast<char*>(ws);
+    double*  l1 = cv.take<double>(n1);
+    double*  l2 = cv.take<double>(n2);
+    double*  l3 = cv.take<double>(n3);
+    double*  om = cv.take<double>(B * 4);
+    double*  db = cv.take<double>(B);
+    int32_t* va = cv.take<int32_t>(B);
+    FPA_TRY(up(l1, d->lambda1, n1 * 8, st));
+    FPA_TRY(up(l2, d->lambda2, n2 * 8, st));
+    FPA_TRY(up(l3, d->lambda3, n3 * 8, st));
+    fpa_plan_desc dd = *d;
+    dd.lambda1 = l1;
+    dd.lambda2 = l2;
+    dd.lambda3 = l3;
+    dd.omega   = d->omega ? om : nullptr;
+    dd.dbeta   = db;
+    dd.valid   = va;
+    FPA_TRY(plan_launch(&dd, nullptr, st));
+    FPA_TRY(down(d->omega, om, B * 32, st));
+    FPA_TRY(down(d->dbeta, db, B * 8, st));
+    FPA_TRY(down(d->valid, va, B * 4, st));
+    FPA_CUDA(cudaStreamSynchronize(st));
+    return FPA_OK;
+}
+
+// ------------------------------------------------------------------ fused sweep
+int64_t fpa_yaman4_sweep_scratch_bytes(int64_t n_points) { return (int64_t)sweep_scratch_need(n_points); }
+
+int fpa_yaman4_sweep_dev(const fpa_sweep_desc* d, void* scratch, int64_t scratch_bytes, void* stream) {
+    if (fpa_device_count() <= 0) {
+        set_error("no CUDA device is visible: libfpa_b200 has no CPU path");
+        return FPA_ERR_NO_DEVICE;
+    }
+    FPA_REQUIRE(scratch != nullptr, "scratch must be set");
+    return sweep_dev(d, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int fpa_yaman4_sweep_host(const fpa_sweep_desc* d, int device) {
+    FPA_REQUIRE(d != nullptr, "sweep descriptor is NULL");
+    const fpa_plan_desc& pl = d->plan;
+    FPA_REQUIRE(pl.n1 >= 0 && pl.n3 >= 0, "grid sizes must be >= 0");
+    FPA_REQUIRE(pl.lambda1 && pl.lambda2 && pl.lambda3, "wavelength axes must be set");
+    FPA_TRY(use_device(device));
+    const size_t n1 = (size_t)pl.n1, n3 = (size_t)pl.n3, B = n1 * n3;
+    if (B == 0) return FPA_OK;
+    FPA_REQUIRE(d->gain_lin != nullptr, "gain_lin must be set");
+    const size_t n2 = pl.lambda2_stride ? n1 : 1;
+    const size_t sweep_bytes = sweep_scratch_need((int64_t)B);
+    size_t need = Carver::need(n1 * 8) + Carver::need(n2 * 8) + Carver::need(n3 * 8) +
+                  Carver::need(B * 8) /*gain*/ + Carver::need(B * 8) /*dbeta*/ +
+                  Carver::need(B * 4) /*valid*/ + Carver::need(B * 4) /*status*/ +
+                  Carver::need(B * 32) /*Pmax*/ + Carver::need(B * 64) /*A_end*/ +
+                  Carver::need(B * 32) /*omega*/ + sweep_bytes;
+    void* ws = nullptr;
+    FPA_TRY(workspace(device, 3, need, &ws));
+    cudaStream_t st;
+    FPA_TRY(host_stream(device, &st));
+    Carver cv;
+    cv.base = static_cast<char*>(ws);
+    double*  l1   = cv.take<double>(n1);
+    double*  l2   = cv.take<double>(n2);
+    double*  l3   = cv.take<double>(n3);
+    double*  gain = cv.take<double>(B);
+    double*  db   = cv.take<double>(B);
+    int32_t* va   = cv.take<int32_t>(B);
+    int32_t* stt  = cv.take<int32_t>(B);
+    double*  Pm   = cv.take<double>(B * 4);
+    double*  Ae   = cv.take<double>(B * 8);
+    double*  om   = cv.take<double>(B * 4);
+    void*    scr  = cv.take<char>(sweep_bytes);
+
+    FPA_TRY(up(l1, pl.lambda1, n1 * 8, st));
+    FPA_TRY(up(l2, pl.lambda2, n2 * 8, st));
+    FPA_TRY(up(l3, pl.lambda3, n3 * 8, st));
+    fpa_sweep_desc dd = *d;
+    dd.plan.lambda1 = l1;
+    dd.plan.lambda2 = l2;
+    dd.plan.lambda3 = l3;
+    dd.plan.omega   = pl.omega ? om : nullptr;
+    dd.plan.dbeta   = db;
+    dd.plan.valid   = va;
+    dd.gain_lin     = gain;
+    dd.Pmax         = d->Pmax ? Pm : nullptr;
+    dd.A_end        = d->A_end ? Ae : nullptr;
+    dd.status       = stt;
+    FPA_TRY(sweep_dev(&dd, scr, (int64_t)sweep_bytes, st));
+    FPA_TRY(down(d->gain_lin, gain, B * 8, st));
+    FPA_TRY(down(pl.dbeta, db, B * 8, st));
+    FPA_TRY(down(pl.valid, va, B * 4, st));
+    FPA_TRY(down(pl.omega, om, B * 32, st));
+    FPA_TRY(down(d->status, stt, B * 4, st));
+    FPA_TRY(down(d->Pmax, Pm, B * 32, st));
+    FPA_TRY(down(d->A_end, Ae, B * 64, st));
+    FPA_CUDA(cudaStreamSynchronize(st));
+    return FPA_OK;
+}
+
+// ------------------------------------------------------------------ linear test RHS
+int fpa_linear_rk4_batch_host(int64_t B, int64_t dim, const double* y0, const double* lam, double z0,
+                              double z_max, int64_t n_steps, int64_t save_every, const double* z_grid,
+                              uint32_t flags, double* y_trace, double* y_end, int32_t* status,
+                              int device) {
+    FPA_REQUIRE(B >= 0 && dim >= 1 && dim < (1 << 20), "need B >= 0 and 1 <= dim < 2^20");
+    FPA_REQUIRE(n_steps >= 1, "n_steps must be >= 1");
+    FPA_REQUIRE(save_every >= 1, "save_every must be a positive integer");
+    FPA_REQUIRE(y0 && lam, "y0 and lam must be set");
+    const bool trace = (flags & FPA_OUT_TRACE) != 0, endo = (flags & FPA_OUT_END) != 0;
+    FPA_REQUIRE(!trace || y_trace, "FPA_OUT_TRACE needs y_trace");
+    FPA_REQUIRE(!endo || y_end, "FPA_OUT_END needs y_end");
+    FPA_TRY(use_device(device));
+    if (B == 0) return FPA_OK;
+    const size_t n = (size_t)B * (size_t)dim, ns = (size_t)fpa_n_saved(n_steps, save_every);
+    const size_t n_grid = z_grid ? (size_t)n_steps + 1 : 0;
+    const size_t n_tr = trace ? n * ns * 2 : 0;
+    void* ws = nullptr;
+    FPA_TRY(workspace(device, 4,
+                      2 * Carver::need(n * 16) + Carver::need((size_t)dim * 16) + Carver::need(n_grid * 8) +
+                          Carver::need(n_tr * 8) + Carver::need(n * 4) + Carver::need((size_t)B * 4),
+                      &ws));
+    cudaStream_t st;
+    FPA_TRY(host_stream(device, &st));
+    Carver cv;
+    cv.base = static_cast<char*>(ws);
+    double*  dy0  = cv.take<double>(n * 2);
+    double*  dye  = cv.take<double>(n * 2);
+    double*  dlam = cv.take<double>((size_t)dim * 2);
+    double*  grid = cv.take<double>(n_grid);
+    double*  dtr  = cv.take<double>(n_tr);
+    int32_t* bad  = cv.take<int32_t>(n);
+    int32_t* stt  = cv.take<int32_t>((size_t)B);
+    FPA_TRY(up(dy0, y0, n * 16, st));
+    FPA_TRY(up(dlam, lam, (size_t)dim * 16, st));
+    FPA_TRY(up(grid, z_grid, n_grid * 8, st));
+    FPA_TRY(linear_launch(B, (int)dim, dy0, dlam, z0, z_max, n_steps, save_every, z_grid ? grid : nullptr,
+                          flags, dtr, dye, bad, stt, st));
+    if (trace) FPA_TRY(down(y_trace, dtr, n_tr * 8, st));
+    if (endo) FPA_TRY(down(y_end, dye, n * 16, st));
+    FPA_TRY(down(status, stt, (size_t)B * 4, st));
+    FPA_CUDA(cudaStreamSynchronize(st));
+    return FPA_OK;
+}
+
+// ------------------------------------------------------------------ N-wave integrator
+int fpa_nwave_rk4_batch_dev(const fpa_nwave_desc* d, void* stream) {
+    if (fpa_device_count() <= 0) {
+        set_error("no CUDA device is visible: libfpa_b200 has no CPU path");
+        return FPA_ERR_NO_DEVICE;
+    }
+    return nwave_launch(d, static_cast<cudaStream_t>(stream));
+}
+
+int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device) {
+    FPA_REQUIRE(d != nullptr, "descriptor is NULL");
+    FPA_REQUIRE(d->n_points >= 0, "n_points must be >= 0");
+    FPA_REQUIRE(d->n_waves >= 1, "n_waves must be >= 1");
+    FPA_REQUIRE(d->n_steps >= 1, "n_steps must be >= 1");
+    FPA_REQUIRE(d->save_every >= 1, "save_every must be a positive integer");
+    FPA_REQUIRE(d->beta && d->gamma && d->alpha && d->A0, "beta/gamma/alpha/A0 must be set");
+    FPA_REQUIRE(d->n_triplets >= 0 && d->row_ptr, "triplet table must be set");
+    FPA_REQUIRE((d->gamma_stride | 1) == 1 && (d->alpha_stride | 1) == 1 && (d->A0_stride | 1) == 1 &&
+                    (d->beta_stride | 1) == 1,
+                "strides must be 0 (broadcast) or 1 (per point)");
+    const bool trace = (d->flags & FPA_OUT_TRACE) != 0, endo = (d->flags & FPA_OUT_END) != 0;
+    const bool pmax = (d->flags & FPA_OUT_PMAX) != 0;
+    FPA_REQUIRE(!trace || d->A_trace, "FPA_OUT_TRACE needs A_trace");
+    FPA_REQUIRE(!pmax || d->Pmax, "FPA_OUT_PMAX needs Pmax");
+    FPA_REQUIRE(!endo || d->A_end, "FPA_OUT_END needs A_end");
+    FPA_TRY(use_device(device));
+    const size_t B = (size_t)d->n_points, N = (size_t)d->n_waves;
+    if (B == 0) return FPA_OK;
+    const size_t ns = (size_t)fpa_n_saved(d->n_steps, d->save_every);
+    const size_t n_b = (d->beta_stride ? B : 1) * N, n_g = d->gamma_stride ? B : 1;
+    const size_t n_a = d->alpha_stride ? B : 1, n_A0 = (d->A0_stride ? B : 1) * N * 2;
+    const size_t n_t = (size_t)d->n_triplets, n_grid = 0;
+    const size_t n_tr = trace ? B * ns * N * 2 : 0;
+    void* ws = nullptr;
+    FPA_TRY(workspace(device, 5,
+                      Carver::need(n_b * 8) + Carver::need(n_g * 8) + Carver::need(n_a * 8) +
+                          Carver::need(n_A0 * 8) + Carver::need(n_t * sizeof(fpa_triplet)) +
+                          Carver::need((N + 1) * 8) + Carver::need(n_grid * 8) + Carver::need(n_tr * 8) +
+                          Carver::need(B * N * 16) + Carver::need(B * N * 8) + Carver::need(B * 4),
+                      &ws));
+    cudaStream_t st;
+    FPA_TRY(host_stream(device, &st));
+    Carver cv;
+    cv.base = static_cast<char*>(ws);
+    double*      beta = cv.take<double>(n_b);
+    double*      gam  = cv.take<double>(n_g);
+    double*      alp  = cv.take<double>(n_a);
+    double*      A0   = cv.take<double>(n_A0);
+    fpa_triplet* tab  = cv.take<fpa_triplet>(n_t);
+    int64_t*     rows = cv.take<int64_t>(N + 1);
+    double*      tr   = cv.take<double>(n_tr);
+    double*      Ae   = cv.take<double>(B * N * 2);
+    double*      Pm   = cv.take<double>(B * N);
+    int32_t*     stt  = cv.take<int32_t>(B);
+    FPA_TRY(up(beta, d->beta, n_b * 8, st));
+    FPA_TRY(up(gam, d->gamma, n_g * 8, st));
+    FPA_TRY(up(alp, d->alpha, n_a * 8, st));
+    FPA_TRY(up(A0, d->A0, n_A0 * 8, st));
+    FPA_TRY(up(tab, d->triplets, n_t * sizeof(fpa_triplet), st));
+    FPA_TRY(up(rows, d->row_ptr, (N + 1) * 8, st));
+    fpa_nwave_desc dd = *d;
+    dd.beta     = beta;
+    dd.gamma    = gam;
+    dd.alpha    = alp;
+    dd.A0       = A0;
+    dd.triplets = tab;
+    dd.row_ptr  = rows;
+    dd.A_trace  = trace ? tr : nullptr;
+    dd.A_end    = endo ? Ae : nullptr;
+    dd.Pmax     = pmax ? Pm : nullptr;
+    dd.status   = stt;
+    // the kernel reads row_ptr on the device but the launcher needs the host copy for sizing
+    FPA_TRY(nwave_launch(&dd, st));
+    if (trace) FPA_TRY(down(d->A_trace, tr, n_tr * 8, st));
+    if (endo) FPA_TRY(down(d->A_end, Ae, B * N * 16, st));
+    if (pmax) FPA_TRY(down(d->Pmax, Pm, B * N * 8, st));
+    FPA_TRY(down(d->status, stt, B * 4, st));
+    FPA_CUDA(cudaStreamSynchronize(st));
+    return FPA_OK;
+}
+
+// ------------------------------------------------------------------ measurement helpers
+int fpa_fp64_peak_probe(int device, int iters, double* tflops, double* ms) {
+    return probe_run(device, iters, tflops, ms);
+}
+
+int fpa_host_alloc(void** ptr, int64_t bytes) {
+    FPA_REQUIRE(ptr != nullptr && bytes >= 0, "bad arguments");
+    if (fpa_device_count() <= 0) {
+        set_error("no CUDA device is visible: pinned host memory needs the CUDA runtime");
+        return FPA_ERR_NO_DEVICE;
+    }
+    FPA_CUDA(cudaMallocHost(ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return FPA_OK;
+}
+
+int fpa_host_free(void* ptr) {
+    if (ptr == nullptr) return FPA_OK;
+    FPA_CUDA(cudaFreeHost(ptr));
+    return FPA_OK;
+}
+
+}  // extern "C"
