@@ -63,6 +63,10 @@ const char* fpa_version(void);
 int fpa_device_count(void);
 /* SM count, max SM clock [kHz] and name of `device`. */
 int fpa_device_info(int device, int* sm_count, int* clock_khz, char* name, int name_cap);
+/* Make `device` current for the calling thread in this library's CUDA runtime.  The *_dev entry
+ * points run on the current device; call this once per thread when the process also uses another
+ * CUDA runtime instance (e.g. PyTorch) to select devices. */
+int fpa_set_device(int device);
 
 /* ------------------------------------------------ 4-wave RK4 integrator (hot path)
  * Replaces the call chain

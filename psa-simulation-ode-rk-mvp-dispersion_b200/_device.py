@@ -151,15 +151,21 @@ def dbeta_table(plan, *, want_omega=False, device: Optional[int] = None) -> dict
     return out
 
 
-def sweep(desc, *, want_pmax=False, want_end=False, device: Optional[int] = None) -> dict:
-    """Run `fpa_yaman4_sweep_host` on a SweepDesc whose plan axes / physics are filled."""
+def sweep(desc, *, want_pmax=False, want_end=False, device: Optional[int] = None,
+          out: Optional[dict] = None) -> dict:
+    """Run `fpa_yaman4_sweep_host` on a SweepDesc whose plan axes / physics are filled.
+    `out` may supply preallocated (e.g. pinned) result arrays gain_lin / dbeta / valid / status."""
     n1, n3 = desc.plan.n1, desc.plan.n3
-    out = {
-        "gain_lin": np.empty((n1, n3)),
-        "dbeta": np.empty((n1, n3)),
-        "valid": np.empty((n1, n3), dtype=np.int32),
-        "status": np.empty((n1, n3), dtype=np.int32),
-    }
+    given = out or {}
+    out = {}
+    for key, dtype in (("gain_lin", np.float64), ("dbeta", np.float64), ("valid", np.int32),
+                       ("status", np.int32)):
+        arr = given.get(key)
+        if arr is None:
+            arr = np.empty((n1, n3), dtype=dtype)
+        elif arr.shape != (n1, n3) or arr.dtype != dtype or not arr.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"out[{key!r}] must be a C-contiguous {np.dtype(dtype)} array of shape {(n1, n3)}")
+        out[key] = arr
     if want_pmax:
         out["Pmax"] = np.empty((n1, n3, 4))
     if want_end:

@@ -102,6 +102,7 @@ SIGNATURES = {
     "fpa_version": (C.c_char_p, []),
     "fpa_device_count": (C.c_int, []),
     "fpa_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]),
+    "fpa_set_device": (C.c_int, [C.c_int]),
     "fpa_n_saved": (C.c_int64, [C.c_int64, C.c_int64]),
     "fpa_interval_steps": (C.c_int64, [C.c_double, C.c_double]),
     "fpa_yaman4_rk4_batch_dev": (C.c_int, [C.POINTER(Yaman4Desc), C.c_void_p]),

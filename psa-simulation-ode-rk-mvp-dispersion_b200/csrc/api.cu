@@ -264,6 +264,8 @@ int fpa_device_info(int device, int* sm_count, int* clock_khz, char* name, int n
     return FPA_OK;
 }
 
+int fpa_set_device(int device) { return use_device(device); }
+
 int64_t fpa_n_saved(int64_t n_steps, int64_t save_every) {
     if (n_steps < 0 || save_every < 1) return -1;
     return n_steps / save_every + 1;

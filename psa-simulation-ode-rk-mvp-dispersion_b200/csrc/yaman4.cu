@@ -106,6 +106,31 @@ __global__ void __launch_bounds__(128, 4) yaman4_rk4_kernel(const Yaman4Params p
         }
     }
 
+    if (nonfinite(dbeta)) {
+        // exp(i*dbeta*z) is NaN from the first stage on: every later sample is NaN and the first
+        // step is the bad one (integrators.py:132-135).  Invalid scan points of a sweep arrive
+        // here with dbeta = NaN and cost nothing.
+        const double qn = qnan();
+        if (TRACE) {
+            double* t = p.A_trace + b * p.n_saved * 8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) store_c128(t + 2 * j, y[2 * j], y[2 * j + 1]);
+            for (int64_t s = 1; s < p.n_saved; ++s)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) store_c128(t + s * 8 + 2 * j, qn, qn);
+        }
+        if (p.A_end)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, qn, qn);
+        if (PMAX) {
+            double2* o = reinterpret_cast<double2*>(p.Pmax + b * 4);
+            o[0] = make_double2(qn, qn);
+            o[1] = make_double2(qn, qn);
+        }
+        if (p.status) p.status[b] = CHECK ? 0 : FPA_POINT_OK;
+        return;
+    }
+
     double* tr = nullptr;
     if (TRACE) {
         tr = p.A_trace + b * p.n_saved * 8;
@@ -144,7 +169,7 @@ __global__ void __launch_bounds__(128, 4) yaman4_rk4_kernel(const Yaman4Params p
         }
         const double h  = zn - zi;  // integrators.py:128
         const double hh = 0.5 * h;
-        const double h6 = h / 6.0;  // integrators.py:59
+        const double h6 = h * (1.0 / 6.0);  // integrators.py:59 (h/6: a 1-ulp difference, no FP64 divide in the loop)
         const double h3 = h6 + h6;
 
         double phr, phi_, p1r, p1i;  // phase at z+h/2 and z+h

@@ -24,13 +24,13 @@ from typing import Literal, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import _device, _lib, constants
+from . import _device, _lib
 from .config import SimulationConfig, custom_simulation_config, validate_config
 from .dispersion import DispersionParams
 from .parameters import FiberParams, SimulationGrid
 from .phase_matching import PhaseMatchingConfig, PhaseMatchingMethod, fill_plan_desc
-from .simulation import (_default_phase_matching_cfg, _length_scale_to_m, _scale_dispersion_to_m,
-                         _scale_phase_matching_cfg_to_m, make_initial_amplitudes, run_batch_simulation)
+from .simulation import (_default_phase_matching_cfg, _length_scale_to_m, make_initial_amplitudes,
+                         run_batch_simulation)
 
 GainMode = Literal["end", "max"]
 
@@ -114,10 +114,11 @@ def sweep_gain_2d(*, cfg: SimulationConfig, lambda_p1_m, lambda_p2_m, lambda_sig
                   alpha: float, p_in, phase_in=None, dispersion: Optional[DispersionParams] = None,
                   phase_matching_cfg: Optional[PhaseMatchingConfig] = None, length_unit: str = "m",
                   gain_unit: str = "dB", phase_exact: bool = False, want_pmax: bool = False,
-                  device: Optional[int] = None) -> dict:
+                  device: Optional[int] = None, out: Optional[dict] = None) -> dict:
     """max-over-saved signal gain and dbeta on the grid lambda_p1[n1] x lambda_signal[n3]
     (lambda_p2 scalar or [n1]).  Returns dict(gain[n1,n3] in gain_unit, gain_lin, dbeta, valid,
-    status, n_steps).  One C-ABI call: axes up, results down."""
+    status, n_steps).  One C-ABI call: axes up, results down.  `out` may hold preallocated
+    (pinned) arrays for gain_lin / dbeta / valid / status."""
     lam3 = _signal_axis(lambda_signal_m)
     lam1 = np.atleast_1d(np.asarray(lambda_p1_m, dtype=float))
     lam2 = np.atleast_1d(np.asarray(lambda_p2_m, dtype=float))
@@ -158,7 +159,7 @@ def sweep_gain_2d(*, cfg: SimulationConfig, lambda_p1_m, lambda_p2_m, lambda_sig
     d.length_scale = s
     d.save_every = int(cfg.save_every)
     d.flags = (_lib.CHECK_NAN if cfg.check_nan else 0) | (_lib.PHASE_EXACT if phase_exact else 0)
-    out = _device.sweep(d, want_pmax=want_pmax, device=device)
+    out = _device.sweep(d, want_pmax=want_pmax, device=device, out=out)
     g = out["gain_lin"]
     with np.errstate(invalid="ignore", divide="ignore"):
         out["gain"] = g if unit == "linear" else 10.0 * np.log10(g)
