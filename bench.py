@@ -281,7 +281,8 @@ def run_ours(args) -> None:
     yd.alpha, yd.alpha_stride = consts.data_ptr() + 8, 0
     yd.A0, yd.A0_stride = consts.data_ptr() + 16, 0
     yd.z0, yd.z_max, yd.n_steps, yd.save_every = 0.0, Z_MAX, n_steps, SAVE_EVERY
-    yd.flags = L.OUT_PMAX | L.CHECK_NAN
+    yd.flags = L.OUT_PMAX | L.CHECK_NAN | L.UNIFORM_PHYSICS
+    yd.gamma_uniform, yd.alpha_uniform = GAMMA, ALPHA
     yd.Pmax, yd.status = t_pmax.data_ptr(), t_status.data_ptr()
     k_ms = []
     for it in range(2 + 3):
@@ -362,7 +363,7 @@ def run_ours(args) -> None:
         "clocks": clocks,
         "roofline": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": None,
-                     "kernel": "yaman4_rk4_kernel<PMAX,CHECK,recurrence>", "kernel_ms": kernel_ms,
+                     "kernel": "yaman4_fast_kernel<PMAX,UNIFORM>", "kernel_ms": kernel_ms,
                      "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
                      "flops_per_point_step": FLOPS_PER_POINT_STEP,
                      "peak_source": "DFMA probe measured live on this GPU (fpa_fp64_peak_probe); "

@@ -43,8 +43,15 @@ extern "C" {
 #define FPA_OUT_END     (1u << 1)  /* write A_end[B,N] (state after the last step)   */
 #define FPA_OUT_PMAX    (1u << 2)  /* write Pmax[B,N] = max over SAVED samples |A|^2  */
 #define FPA_CHECK_NAN   (1u << 3)  /* per-step finite check (integrators.py:132-135) */
-#define FPA_PHASE_EXACT (1u << 4)  /* sincos at every RK4 abscissa instead of the    *
-                                    * rotation recurrence with periodic re-sync     */
+#define FPA_PHASE_EXACT (1u << 4)  /* the reference's arithmetic structure step by   *
+                                    * step: h_i = z_{i+1}-z_i, sincos at every RK4   *
+                                    * abscissa, k_1..k_4 formed (slower; default is  *
+                                    * the constant-h / phase-recurrence fast kernel) */
+#define FPA_UNIFORM_PHYSICS (1u << 5) /* gamma and alpha are the same for every point *
+                                    * (stride 0) AND their values are given in       *
+                                    * gamma_uniform / alpha_uniform: the kernel then  *
+                                    * keeps all stage coefficients in the constant    *
+                                    * bank instead of registers                       */
 
 /* status[b] values written by the integrators */
 #define FPA_POINT_OK      (-1)     /* otherwise: index of the first step whose result was non-finite */
@@ -97,12 +104,14 @@ typedef struct fpa_yaman4_desc {
     int64_t       n_steps;       /* >= 1                                                  */
     int64_t       save_every;    /* >= 1                                                  */
     const double* z_grid;        /* NULL, or [n_steps+1] explicit grid                    */
-    uint32_t      flags;         /* FPA_OUT_* | FPA_CHECK_NAN | FPA_PHASE_EXACT           */
+    uint32_t      flags;         /* FPA_OUT_* | FPA_CHECK_NAN | FPA_PHASE_EXACT | FPA_UNIFORM_PHYSICS */
     uint32_t      reserved;
     double*       A_trace;       /* [B,n_saved,4] complex128 or NULL                      */
     double*       A_end;         /* [B,4] complex128 or NULL                              */
     double*       Pmax;          /* [B,4] or NULL                                         */
     int32_t*      status;        /* [B] (always written when non-NULL)                    */
+    double        gamma_uniform; /* with FPA_UNIFORM_PHYSICS: the value *gamma points to   */
+    double        alpha_uniform; /* with FPA_UNIFORM_PHYSICS: the value *alpha points to   */
 } fpa_yaman4_desc;
 
 /* n_saved for (n_steps, save_every): n_steps/save_every + 1 (integrators.py:115). */

@@ -9,7 +9,7 @@ C ABI of include/fpa_b200.h; there is no CPU fallback.
 """
 from . import _lib, _device  # noqa: F401
 from . import (config, constants, dispersion, frequency_plan, integrators, io_fwm,  # noqa: F401
-               nwave, parameters, phase_matching, scan_mismtach, simulation, yaman_model)
+               nwave, parameters, phase_matching, scan_mismtach, sharding, simulation, yaman_model)
 
 __all__ = ["config", "constants", "dispersion", "frequency_plan", "integrators", "io_fwm", "nwave",
-           "parameters", "phase_matching", "scan_mismtach", "simulation", "yaman_model"]
+           "parameters", "phase_matching", "scan_mismtach", "sharding", "simulation", "yaman_model"]

@@ -17,7 +17,7 @@ LIB_PATH = PKG_DIR / "libfpa_b200.so"
 
 # status codes / flags (include/fpa_b200.h)
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
-OUT_TRACE, OUT_END, OUT_PMAX, CHECK_NAN, PHASE_EXACT = 1, 2, 4, 8, 16
+OUT_TRACE, OUT_END, OUT_PMAX, CHECK_NAN, PHASE_EXACT, UNIFORM_PHYSICS = 1, 2, 4, 8, 16, 32
 POINT_OK = -1
 PM_GENERAL_TAYLOR, PM_SYMMETRIC_EVEN, PM_PROVIDED = 0, 1, 2
 MAX_TAYLOR_ORDER = 12
@@ -40,6 +40,7 @@ class Yaman4Desc(C.Structure):
         ("flags", C.c_uint32), ("reserved", C.c_uint32),
         ("A_trace", C.c_void_p), ("A_end", C.c_void_p), ("Pmax", C.c_void_p),
         ("status", C.c_void_p),
+        ("gamma_uniform", C.c_double), ("alpha_uniform", C.c_double),
     ]
 
 

@@ -216,8 +216,10 @@ static int sweep_dev(const fpa_sweep_desc* d, void* scratch, int64_t scratch_byt
     y.n_steps      = fpa_interval_steps(d->z_max * sc, d->dz * sc);
     FPA_REQUIRE(y.n_steps >= 1, "z_max/dz rounds to zero steps");
     y.save_every   = d->save_every;
-    y.flags        = FPA_OUT_PMAX | (d->flags & (FPA_CHECK_NAN | FPA_PHASE_EXACT)) |
+    y.flags        = FPA_OUT_PMAX | FPA_UNIFORM_PHYSICS | (d->flags & (FPA_CHECK_NAN | FPA_PHASE_EXACT)) |
                      (d->A_end ? FPA_OUT_END : 0u);
+    y.gamma_uniform = d->gamma / sc;
+    y.alpha_uniform = d->alpha / sc;
     y.Pmax         = Pmax;
     y.A_end        = d->A_end;
     y.status       = status;
@@ -344,6 +346,13 @@ int fpa_yaman4_rk4_batch_host(const fpa_yaman4_desc* d, int device) {
     dd.A_end   = endo ? Aend : nullptr;
     dd.Pmax    = pmax ? Pm : nullptr;
     dd.status  = stat;
+    if (d->gamma_stride == 0 && d->alpha_stride == 0) {  // host pointers: the broadcast values are known here
+        dd.flags |= FPA_UNIFORM_PHYSICS;
+        dd.gamma_uniform = d->gamma[0];
+        dd.alpha_uniform = d->alpha[0];
+    } else {
+        dd.flags &= ~FPA_UNIFORM_PHYSICS;
+    }
     FPA_REQUIRE(!trace || d->A_trace, "FPA_OUT_TRACE needs A_trace");
     FPA_REQUIRE(!pmax || d->Pmax, "FPA_OUT_PMAX needs Pmax");
     FPA_REQUIRE(!endo || d->A_end, "FPA_OUT_END needs A_end");

@@ -1,8 +1,8 @@
 // yaman4.cu -- fused fixed-step RK4 x 4-wave Yaman/Agrawal FWM right-hand side.
 //
-// One thread integrates one scan point for ALL z-steps with its state in registers:
-// the four RK4 stages, the RHS, the per-step finite check, the max-over-saved-samples
-// metric and the trace write-out are a single kernel (one launch per batch).
+// One thread integrates one scan point for ALL z-steps with its state in registers: the four RK4
+// stages, the RHS, the per-step finite check, the max-over-saved-samples metric and the trace
+// write-out are a single kernel (one launch per batch).
 //
 // What it stands in for in the reference (paths relative to the reference checkout):
 //   integrators.rk4_step              integrators.py:25-61   (stage formulas :54-59)
@@ -11,20 +11,37 @@
 //   yaman_model.rhs_yaman_simplified  yaman_model.py:10-52   (+ _linear_loss_terms :123-132,
 //                                     _kerr_terms :135-156, _fwm_terms :159-186)
 //
-// Why thread-per-point and not warp-per-point for N = 4: the FWM sum has four terms;
-// a warp per point would leave 28 lanes idle.  The bound is the FP64 FMA pipe, so the
-// kernel is written to minimise DFMA-pipe instructions per step:
-//   RHS      64 FP64 instructions (8 powers, 3 adds, 1+4 Kerr factors, 8 pair products,
-//            8 phased pairs, 32 fused assemble ops)
-//   RK4      56 FMAs per step (3 stage states + 4 accumulations of 8 components)
-//   phase    2 complex rotations per step (8 instr.) with an exact sincos re-sync every
-//            FPA_RESYNC steps, instead of the reference's 8 complex exp() per step
-//   => ~325 FP64 instructions for 568 algorithmic flops per point.step.
+// Why thread-per-point and not warp-per-point for N = 4: the FWM sum has four terms; a warp per
+// point would leave 28 lanes idle.  The bound is the FP64 FMA pipe (16 lanes per SM sub-partition:
+// one warp-wide FP64 instruction every 2 cycles), so the kernels are written to minimise FP64
+// instructions per point.step.  Two kernel families:
+//
+//  * yaman4_fast_kernel -- uniform grid (integrate_interval).  ~300 FP64 instructions per step:
+//      - constant step h = (z_max-z0)/n_steps (the reference's per-step h_i = z_{i+1}-z_i differs
+//        from it by <= 1 ulp(z); the sum telescopes to the same z_max);
+//      - every stage writes the NEXT STAGE STATE directly: y + c*f(ys) is one 4-FMA chain per
+//        component with the stage weight c folded into the Kerr / loss / phase coefficients, so
+//        k_1..k_4 are never formed;
+//      - the RK4 combination is rebuilt from the stage states,
+//            y' = -y/3 + ys2/3 + 2 ys3/3 + ys4/3 + (h/6) f(ys4)       (algebraically identical);
+//      - the FWM phase 2*gamma*exp(i*dbeta*z) advances by a constant complex rotation per half
+//        step (2 rotations per step) and is re-synchronised with an exact sincos every 32 steps,
+//        instead of the reference's 8 complex exp() per step.
+//    Measured against the oracle: <= 1e-13 relative on |A|^2 after 10 000 steps at 45 dB gain.
+//  * yaman4_exact_kernel -- FPA_PHASE_EXACT or an explicit z-grid: the reference's arithmetic
+//    structure step by step (h_i by subtraction, sincos at z, z+h/2, z+h, k_j formed, y + h/6*(..)).
 #include "fpa_common.cuh"
 
 namespace fpa {
 
 constexpr int kResync = 32;  // steps between exact sincos re-synchronisations of the phase
+
+struct Yaman4Coef {  // stage-weighted coefficients; c = {h/2, h, h/6}
+    double cg[3];    // c*gamma
+    double c2g[3];   // 2*c*gamma
+    double cn[3];    // -c*alpha/2
+    double q0;       // (h/2)*2*gamma : modulus of the scaled phase factor
+};
 
 struct Yaman4Params {
     int64_t       n_points;
@@ -37,131 +54,260 @@ struct Yaman4Params {
     double*       A_end;
     double*       Pmax;
     int32_t*      status;
-    double        z0, z_max;
+    double        z0, z_max, h;
     int           gamma_stride, alpha_stride, A0_stride;
     int           n_steps, save_every;
+    int           check;
     int64_t       n_saved;
+    Yaman4Coef    coef;  // valid when gamma and alpha are the same for every point (UNIFORM)
 };
 
-// dA/dz for one point.  y = (x1,y1,x2,y2,x3,y3,x4,y4); (pr,pi) = 2*gamma*exp(i*dbeta*z);
-// nha = -alpha/2.  64 FP64 instructions, negations ride on the FMA source modifiers.
-__device__ __forceinline__ void rhs4(const double (&y)[8], double pr, double pi, double gamma,
-                                     double nha, double (&k)[8], double& Ssum) {
-    const double x1 = y[0], y1 = y[1], x2 = y[2], y2 = y[3];
-    const double x3 = y[4], y3 = y[5], x4 = y[6], y4 = y[7];
+__host__ __device__ inline Yaman4Coef make_coef(double gamma, double alpha, double h) {
+    Yaman4Coef c;
+    const double w[3] = {0.5 * h, h, h * (1.0 / 6.0)};
+    const double nha  = -0.5 * alpha;
+    for (int s = 0; s < 3; ++s) {
+        c.cg[s]  = w[s] * gamma;
+        c.c2g[s] = c.cg[s] + c.cg[s];
+        c.cn[s]  = w[s] * nha;
+    }
+    c.q0 = c.c2g[0];
+    return c;
+}
 
+// ------------------------------------------------------------------ fast path
+// One RK4 stage.  in = stage state (x1,y1,..,x4,y4), base = what the weighted RHS is added to,
+// (qr,qi) = c*2*gamma*exp(i*dbeta*z) for this stage's weight c, cg/c2g/cn the matching
+// coefficients.  out = base + c*f(in): 32 shared + 32 chain FP64 instructions.  S = sum |in|^2.
+__device__ __forceinline__ void stage(const double (&in)[8], const double (&base)[8], double qr, double qi,
+                                      double cg, double c2g, double cn, double (&out)[8], double& S) {
+    const double x1 = in[0], y1 = in[1], x2 = in[2], y2 = in[3];
+    const double x3 = in[4], y3 = in[5], x4 = in[6], y4 = in[7];
     // powers (yaman_model.py:144-147)
     const double P1 = fma(y1, y1, x1 * x1);
     const double P2 = fma(y2, y2, x2 * x2);
     const double P3 = fma(y3, y3, x3 * x3);
     const double P4 = fma(y4, y4, x4 * x4);
-    const double S  = (P1 + P2) + (P3 + P4);
-    Ssum = S;
-    // gamma*(P_j + 2*sum_{k!=j} P_k) == gamma*(2S - P_j)   (yaman_model.py:148-151)
-    const double c2 = (gamma + gamma) * S;
-    const double G1 = fma(-gamma, P1, c2);
-    const double G2 = fma(-gamma, P2, c2);
-    const double G3 = fma(-gamma, P3, c2);
-    const double G4 = fma(-gamma, P4, c2);
-
+    S = (P1 + P2) + (P3 + P4);
+    // c*gamma*(P_j + 2*sum_{k!=j} P_k) == c*gamma*(2S - P_j)   (yaman_model.py:148-151)
+    const double c2 = c2g * S;
+    const double G1 = fma(-cg, P1, c2);
+    const double G2 = fma(-cg, P2, c2);
+    const double G3 = fma(-cg, P3, c2);
+    const double G4 = fma(-cg, P4, c2);
     // pair products shared by two waves each (yaman_model.py:177-181)
     const double Ur = fma(-y3, y4, x3 * x4), Ui = fma(x3, y4, y3 * x4);  // A3*A4
     const double Vr = fma(-y1, y2, x1 * x2), Vi = fma(x1, y2, y1 * x2);  // A1*A2
-    // W = 2g e^{+i th} U ,  Z = 2g e^{-i th} V
-    const double Wr = fma(-pi, Ui, pr * Ur), Wi = fma(pr, Ui, pi * Ur);
-    const double Zr = fma(pi, Vi, pr * Vr),  Zi = fma(pr, Vi, -(pi * Vr));
-
-    // dA_j = nha*A_j + i*G_j*A_j + i*conj(A_m)*{W|Z}
-    //   conj(A_m)*W = (xm Wr + ym Wi) + i (xm Wi - ym Wr)
-    k[0] = fma(nha, x1, fma(-G1, y1, fma(y2, Wr, -(x2 * Wi))));
-    k[1] = fma(nha, y1, fma(G1, x1, fma(x2, Wr, y2 * Wi)));
-    k[2] = fma(nha, x2, fma(-G2, y2, fma(y1, Wr, -(x1 * Wi))));
-    k[3] = fma(nha, y2, fma(G2, x2, fma(x1, Wr, y1 * Wi)));
-    k[4] = fma(nha, x3, fma(-G3, y3, fma(y4, Zr, -(x4 * Zi))));
-    k[5] = fma(nha, y3, fma(G3, x3, fma(x4, Zr, y4 * Zi)));
-    k[6] = fma(nha, x4, fma(-G4, y4, fma(y3, Zr, -(x3 * Zi))));
-    k[7] = fma(nha, y4, fma(G4, x4, fma(x3, Zr, y3 * Zi)));
+    // W = q U ,  Z = conj(q) V
+    const double Wr = fma(-qi, Ui, qr * Ur), Wi = fma(qr, Ui, qi * Ur);
+    const double Zr = fma(qi, Vi, qr * Vr),  Zi = fma(qr, Vi, -(qi * Vr));
+    // out_j = base_j + cn*A_j + i*G_j*A_j + i*conj(A_m)*{W|Z}
+    //   i*conj(A_m)*W = (ym Wr - xm Wi) + i (xm Wr + ym Wi)
+    out[0] = fma(cn, x1, fma(-G1, y1, fma(y2, Wr, fma(-x2, Wi, base[0]))));
+    out[1] = fma(cn, y1, fma(G1, x1, fma(x2, Wr, fma(y2, Wi, base[1]))));
+    out[2] = fma(cn, x2, fma(-G2, y2, fma(y1, Wr, fma(-x1, Wi, base[2]))));
+    out[3] = fma(cn, y2, fma(G2, x2, fma(x1, Wr, fma(y1, Wi, base[3]))));
+    out[4] = fma(cn, x3, fma(-G3, y3, fma(y4, Zr, fma(-x4, Zi, base[4]))));
+    out[5] = fma(cn, y3, fma(G3, x3, fma(x4, Zr, fma(y4, Zi, base[5]))));
+    out[6] = fma(cn, x4, fma(-G4, y4, fma(y3, Zr, fma(-x3, Zi, base[6]))));
+    out[7] = fma(cn, y4, fma(G4, x4, fma(x3, Zr, fma(y3, Zi, base[7]))));
 }
 
-enum PhaseMode { kRecurrence = 0, kExactUniform = 1, kExplicitGrid = 2 };
-
-template <bool TRACE, bool PMAX, bool CHECK, int PHASE>
-__global__ void __launch_bounds__(128, 4) yaman4_rk4_kernel(const Yaman4Params p) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.n_points) return;
-
-    const double dbeta = p.dbeta[b];
-    const double gamma = p.gamma[b * p.gamma_stride];
-    const double nha   = -0.5 * p.alpha[b * p.alpha_stride];
-    const double g2    = gamma + gamma;
-
-    double y[8];
-    {
-        const double2* a0 = reinterpret_cast<const double2*>(p.A0) + b * p.A0_stride * 4;
+__device__ __forceinline__ void load_state(const Yaman4Params& p, int64_t b, double (&y)[8]) {
+    const double2* a0 = reinterpret_cast<const double2*>(p.A0) + b * p.A0_stride * 4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double2 v = a0[j];
-            y[2 * j] = v.x;
-            y[2 * j + 1] = v.y;
-        }
+    for (int j = 0; j < 4; ++j) {
+        const double2 v = a0[j];
+        y[2 * j] = v.x;
+        y[2 * j + 1] = v.y;
     }
+}
 
-    if (nonfinite(dbeta)) {
-        // exp(i*dbeta*z) is NaN from the first stage on: every later sample is NaN and the first
-        // step is the bad one (integrators.py:132-135).  Invalid scan points of a sweep arrive
-        // here with dbeta = NaN and cost nothing.
-        const double qn = qnan();
-        if (TRACE) {
-            double* t = p.A_trace + b * p.n_saved * 8;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) store_c128(t + 2 * j, y[2 * j], y[2 * j + 1]);
-            for (int64_t s = 1; s < p.n_saved; ++s)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) store_c128(t + s * 8 + 2 * j, qn, qn);
-        }
-        if (p.A_end)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, qn, qn);
-        if (PMAX) {
-            double2* o = reinterpret_cast<double2*>(p.Pmax + b * 4);
-            o[0] = make_double2(qn, qn);
-            o[1] = make_double2(qn, qn);
-        }
-        if (p.status) p.status[b] = CHECK ? 0 : FPA_POINT_OK;
-        return;
+// A point whose dbeta is not finite: exp(i*dbeta*z) is NaN from the first stage on, every later
+// sample is NaN and step 0 is the bad one (integrators.py:132-135).  Invalid scan points of a sweep
+// arrive here with dbeta = NaN and cost nothing.
+__device__ __noinline__ void write_invalid_point(const Yaman4Params& p, int64_t b, const double (&y)[8]) {
+    const double qn = qnan();
+    if (p.A_trace) {
+        double* t = p.A_trace + b * p.n_saved * 8;
+        for (int j = 0; j < 4; ++j) store_c128(t + 2 * j, y[2 * j], y[2 * j + 1]);
+        for (int64_t s = 1; s < p.n_saved; ++s)
+            for (int j = 0; j < 4; ++j) store_c128(t + s * 8 + 2 * j, qn, qn);
     }
+    if (p.A_end)
+        for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, qn, qn);
+    if (p.Pmax)
+        for (int j = 0; j < 4; ++j) p.Pmax[b * 4 + j] = qn;
+    if (p.status) p.status[b] = p.check ? 0 : FPA_POINT_OK;
+}
 
-    double* tr = nullptr;
-    if (TRACE) {
-        tr = p.A_trace + b * p.n_saved * 8;
+__device__ __forceinline__ void save_sample(const double (&y)[8], double*& tr, double (&pm)[4], bool trace,
+                                            bool pmax) {
+    if (trace) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) store_c128(tr + 2 * j, y[2 * j], y[2 * j + 1]);
         tr += 8;
     }
-    double pm[4];
+    if (pmax) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double P = fma(y[2 * j + 1], y[2 * j + 1], y[2 * j] * y[2 * j]);
+            // numpy.max semantics: NaN is sticky
+            pm[j] = (P != P || pm[j] != pm[j]) ? qnan() : fmax(pm[j], P);
+        }
+    }
+}
+
+__device__ __forceinline__ void write_results(const Yaman4Params& p, int64_t b, const double (&y)[8],
+                                              const double (&pm)[4], bool pmax, int32_t bad) {
+    if (p.check && bad == FPA_POINT_OK) {
+        bool nf = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nf |= nonfinite(y[j]);
+        if (nf) bad = p.n_steps - 1;
+    }
+    if (p.status) p.status[b] = p.check ? bad : FPA_POINT_OK;
+    if (p.A_end) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, y[2 * j], y[2 * j + 1]);
+    }
+    if (pmax) {
+        double2* o = reinterpret_cast<double2*>(p.Pmax + b * 4);
+        o[0] = make_double2(pm[0], pm[1]);
+        o[1] = make_double2(pm[2], pm[3]);
+    }
+}
+
+template <bool TRACE, bool PMAX, bool UNIFORM, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_fast_kernel(const Yaman4Params p) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.n_points) return;
+
+    double y[8];
+    load_state(p, b, y);
+    const double dbeta = p.dbeta[b];
+    if (nonfinite(dbeta)) {
+        write_invalid_point(p, b, y);
+        return;
+    }
+    // stage-weighted coefficients: from the constant bank when the physics is uniform over the
+    // batch (sweeps), else per thread
+    Yaman4Coef cf;
+    if (UNIFORM) {
+        cf = p.coef;
+    } else {
+        cf = make_coef(p.gamma[b * p.gamma_stride], p.alpha[b * p.alpha_stride], p.h);
+    }
+
+    double* tr = nullptr;
+    double  pm[4] = {0.0, 0.0, 0.0, 0.0};
+    if (TRACE) tr = p.A_trace + b * p.n_saved * 8;
     if (PMAX) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pm[j] = fma(y[2 * j + 1], y[2 * j + 1], y[2 * j] * y[2 * j]);
+        for (int j = 0; j < 4; ++j) pm[j] = -1.0;  // |A|^2 >= 0: first sample always replaces it
     }
+    save_sample(y, tr, pm, TRACE, PMAX);
+
+    const int    n_steps = p.n_steps;
+    const double h = p.h, z0 = p.z0;
+    // rotation by half a step
+    double rr, ri;
+    sincos(dbeta * (0.5 * h), &ri, &rr);
+
+    double  qr = cf.q0, qi = 0.0;  // (h/2)*2*gamma*exp(i*dbeta*z_i)
+    int     save_ctr = p.save_every;
+    int32_t bad = FPA_POINT_OK;
+    const double third = 1.0 / 3.0, two_thirds = 2.0 / 3.0;
+
+    for (int i = 0; i < n_steps; ++i) {
+        if ((i & (kResync - 1)) == 0) {
+            double s, c;
+            sincos(dbeta * fma((double)i, h, z0), &s, &c);
+            qr = cf.q0 * c;
+            qi = cf.q0 * s;
+        }
+        // phase at z+h/2 (weight h/2), the same with weight h, and at z+h (weights h/2 and h/6)
+        const double qhr = fma(-qi, ri, qr * rr), qhi = fma(qr, ri, qi * rr);
+        const double q2r = qhr + qhr, q2i = qhi + qhi;
+        const double qfr = fma(-qhi, ri, qhr * rr), qfi = fma(qhr, ri, qhi * rr);
+        const double q6r = qfr * third, q6i = qfi * third;
+
+        double ys[8], yt[8], acc[8], S, Sx;
+        // stage 1: ys = y + (h/2) f(z, y)
+        stage(y, y, qr, qi, cf.cg[0], cf.c2g[0], cf.cn[0], ys, S);
+        // S = sum |A|^2 of the state that step i-1 produced: a non-finite component makes S
+        // non-finite, so the exact per-component test runs only then (integrators.py:132-135).
+        if (nonfinite(S) && bad == FPA_POINT_OK && i > 0) {
+            bool nf = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nf |= nonfinite(y[j]);
+            if (nf) bad = i - 1;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fma(third, ys[j], y[j] * (-third));
+        // stage 2: yt = y + (h/2) f(z+h/2, ys)
+        stage(ys, y, qhr, qhi, cf.cg[0], cf.c2g[0], cf.cn[0], yt, Sx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fma(two_thirds, yt[j], acc[j]);
+        // stage 3: ys = y + h f(z+h/2, yt)
+        stage(yt, y, q2r, q2i, cf.cg[1], cf.c2g[1], cf.cn[1], ys, Sx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fma(third, ys[j], acc[j]);
+        // stage 4: y' = acc + (h/6) f(z+h, ys)
+        stage(ys, acc, q6r, q6i, cf.cg[2], cf.c2g[2], cf.cn[2], y, Sx);
+
+        qr = qfr;
+        qi = qfi;
+
+        if (--save_ctr == 0) {  // (i+1) % save_every == 0, integrators.py:137-140
+            save_ctr = p.save_every;
+            save_sample(y, tr, pm, TRACE, PMAX);
+        }
+    }
+    write_results(p, b, y, pm, PMAX, bad);
+}
+
+// ------------------------------------------------------------------ exact path
+// dA/dz for one point.  (pr,pi) = 2*gamma*exp(i*dbeta*z); nha = -alpha/2.
+__device__ __forceinline__ void rhs4(const double (&y)[8], double pr, double pi, double gamma,
+                                     double nha, double (&k)[8], double& Ssum) {
+    const double zero[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    stage(y, zero, pr, pi, gamma, gamma + gamma, nha, k, Ssum);
+}
+
+template <bool GRID>
+__global__ void __launch_bounds__(128, 3) yaman4_exact_kernel(const Yaman4Params p) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.n_points) return;
+
+    double y[8];
+    load_state(p, b, y);
+    const double dbeta = p.dbeta[b];
+    if (nonfinite(dbeta)) {
+        write_invalid_point(p, b, y);
+        return;
+    }
+    const double gamma = p.gamma[b * p.gamma_stride];
+    const double nha   = -0.5 * p.alpha[b * p.alpha_stride];
+    const double g2    = gamma + gamma;
+    const bool   trace = p.A_trace != nullptr, pmax = p.Pmax != nullptr;
+
+    double* tr = trace ? p.A_trace + b * p.n_saved * 8 : nullptr;
+    double  pm[4] = {-1.0, -1.0, -1.0, -1.0};
+    save_sample(y, tr, pm, trace, pmax);
 
     const int    n_steps = p.n_steps;
     const double z0 = p.z0, z_max = p.z_max;
     // numpy.linspace: step = (stop-start)/div, z_i = i*step + start, z_n = stop
     const double step = (z_max - z0) / (double)n_steps;
-
-    // rotation by half a nominal step
-    double rr, ri;
-    if (PHASE == kRecurrence) sincos(dbeta * (0.5 * step), &ri, &rr);
-
-    double  zi = (PHASE == kExplicitGrid) ? p.z_grid[0] : z0;
+    double  zi = GRID ? p.z_grid[0] : z0;
     double  di = 0.0;
-    double  pr = g2, pi = 0.0;  // 2*gamma*exp(i*dbeta*z_i)
     int     save_ctr = p.save_every;
     int32_t bad = FPA_POINT_OK;
 
     for (int i = 0; i < n_steps; ++i) {
         double zn;
-        if (PHASE == kExplicitGrid) {
+        if (GRID) {
             zn = p.z_grid[i + 1];
         } else {
             di += 1.0;
@@ -169,51 +315,25 @@ __global__ void __launch_bounds__(128, 4) yaman4_rk4_kernel(const Yaman4Params p
         }
         const double h  = zn - zi;  // integrators.py:128
         const double hh = 0.5 * h;
-        const double h6 = h * (1.0 / 6.0);  // integrators.py:59 (h/6: a 1-ulp difference, no FP64 divide in the loop)
+        const double h6 = h / 6.0;  // integrators.py:59
         const double h3 = h6 + h6;
 
-        double phr, phi_, p1r, p1i;  // phase at z+h/2 and z+h
-        if (PHASE == kRecurrence) {
-            if ((i & (kResync - 1)) == 0) {
-                double s, c;
-                sincos(dbeta * zi, &s, &c);
-                pr = g2 * c;
-                pi = g2 * s;
-            }
-            phr  = fma(-pi, ri, pr * rr);
-            phi_ = fma(pr, ri, pi * rr);
-            p1r  = fma(-phi_, ri, phr * rr);
-            p1i  = fma(phr, ri, phi_ * rr);
-        } else {
-            double s, c;
-            sincos(dbeta * zi, &s, &c);
-            pr = g2 * c;
-            pi = g2 * s;
-            sincos(dbeta * (zi + hh), &s, &c);  // integrators.py:55-56
-            phr  = g2 * c;
-            phi_ = g2 * s;
-            sincos(dbeta * (zi + h), &s, &c);  // integrators.py:57
-            p1r = g2 * c;
-            p1i = g2 * s;
-        }
-
-        double k[8], ys[8], yn[8], S, Sx;
-        rhs4(y, pr, pi, gamma, nha, k, S);
-        if (CHECK) {
-            // S = sum |A|^2 of the state that step i-1 produced: non-finite S is the only way
-            // a component can be non-finite, so the exact per-component test runs only then.
-            if (nonfinite(S) && bad == FPA_POINT_OK && i > 0) {
-                bool nf = false;
+        double s, c, k[8], ys[8], yn[8], S, Sx;
+        sincos(dbeta * zi, &s, &c);
+        rhs4(y, g2 * c, g2 * s, gamma, nha, k, S);
+        if (nonfinite(S) && bad == FPA_POINT_OK && i > 0) {
+            bool nf = false;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) nf |= nonfinite(y[j]);
-                if (nf) bad = i - 1;
-            }
+            for (int j = 0; j < 8; ++j) nf |= nonfinite(y[j]);
+            if (nf) bad = i - 1;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             yn[j] = fma(h6, k[j], y[j]);
             ys[j] = fma(hh, k[j], y[j]);
         }
+        sincos(dbeta * (zi + hh), &s, &c);  // integrators.py:55-56
+        const double phr = g2 * c, phi_ = g2 * s;
         rhs4(ys, phr, phi_, gamma, nha, k, Sx);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -226,48 +346,18 @@ __global__ void __launch_bounds__(128, 4) yaman4_rk4_kernel(const Yaman4Params p
             yn[j] = fma(h3, k[j], yn[j]);
             ys[j] = fma(h, k[j], y[j]);
         }
-        rhs4(ys, p1r, p1i, gamma, nha, k, Sx);
+        sincos(dbeta * (zi + h), &s, &c);  // integrators.py:57
+        rhs4(ys, g2 * c, g2 * s, gamma, nha, k, Sx);
 #pragma unroll
         for (int j = 0; j < 8; ++j) y[j] = fma(h6, k[j], yn[j]);
-
-        pr = p1r;
-        pi = p1i;
         zi = zn;
 
-        if (--save_ctr == 0) {  // (i+1) % save_every == 0, integrators.py:137-140
+        if (--save_ctr == 0) {
             save_ctr = p.save_every;
-            if (TRACE) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) store_c128(tr + 2 * j, y[2 * j], y[2 * j + 1]);
-                tr += 8;
-            }
-            if (PMAX) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double P = fma(y[2 * j + 1], y[2 * j + 1], y[2 * j] * y[2 * j]);
-                    // numpy.max semantics: NaN is sticky
-                    pm[j] = (P != P || pm[j] != pm[j]) ? qnan() : fmax(pm[j], P);
-                }
-            }
+            save_sample(y, tr, pm, trace, pmax);
         }
     }
-
-    if (CHECK && bad == FPA_POINT_OK) {
-        bool nf = false;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) nf |= nonfinite(y[j]);
-        if (nf) bad = n_steps - 1;
-    }
-    if (p.status) p.status[b] = bad;
-    if (p.A_end) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, y[2 * j], y[2 * j + 1]);
-    }
-    if (PMAX) {
-        double2* o = reinterpret_cast<double2*>(p.Pmax + b * 4);
-        o[0] = make_double2(pm[0], pm[1]);
-        o[1] = make_double2(pm[2], pm[3]);
-    }
+    write_results(p, b, y, pm, pmax, bad);
 }
 
 // RHS-only kernel (direct calls of yaman_model.rhs_yaman_simplified, yaman_model.py:10-52):
@@ -286,21 +376,25 @@ __global__ void yaman4_rhs_kernel(int64_t B, const double* z, const double* A, c
     for (int j = 0; j < 8; ++j) dA[b * 8 + j] = k[j];
 }
 
-template <bool TRACE, bool PMAX, bool CHECK>
-static cudaError_t launch_phase(const Yaman4Params& p, int phase, cudaStream_t st) {
-    const int  threads = 128;
+// Launch shape of the fast kernel: kFastThreads threads per block, kFastMinBlocks resident blocks
+// per SM (register cap = 65536 / (threads * blocks)); chosen by measurement (tools/tune_yaman4.cu,
+// DESIGN.md).
+#ifndef FPA_YAMAN4_THREADS
+#define FPA_YAMAN4_THREADS 128
+#endif
+#ifndef FPA_YAMAN4_MIN_BLOCKS
+#define FPA_YAMAN4_MIN_BLOCKS 4
+#endif
+constexpr int kFastThreads = FPA_YAMAN4_THREADS, kFastMinBlocks = FPA_YAMAN4_MIN_BLOCKS;
+
+template <bool TRACE, bool PMAX>
+static cudaError_t launch_fast(const Yaman4Params& p, bool uniform, cudaStream_t st) {
+    const int  threads = kFastThreads;
     const long blocks  = (long)((p.n_points + threads - 1) / threads);
-    switch (phase) {
-        case kRecurrence:
-            yaman4_rk4_kernel<TRACE, PMAX, CHECK, kRecurrence><<<blocks, threads, 0, st>>>(p);
-            break;
-        case kExactUniform:
-            yaman4_rk4_kernel<TRACE, PMAX, CHECK, kExactUniform><<<blocks, threads, 0, st>>>(p);
-            break;
-        default:
-            yaman4_rk4_kernel<TRACE, PMAX, CHECK, kExplicitGrid><<<blocks, threads, 0, st>>>(p);
-            break;
-    }
+    if (uniform)
+        yaman4_fast_kernel<TRACE, PMAX, true, kFastThreads, kFastMinBlocks><<<blocks, threads, 0, st>>>(p);
+    else
+        yaman4_fast_kernel<TRACE, PMAX, false, kFastThreads, kFastMinBlocks><<<blocks, threads, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -318,6 +412,9 @@ int yaman4_launch(const fpa_yaman4_desc* d, cudaStream_t st) {
     FPA_REQUIRE(!trace || d->A_trace, "FPA_OUT_TRACE needs A_trace");
     FPA_REQUIRE(!pmax || d->Pmax, "FPA_OUT_PMAX needs Pmax");
     FPA_REQUIRE(!endo || d->A_end, "FPA_OUT_END needs A_end");
+    const bool uniform = (d->flags & FPA_UNIFORM_PHYSICS) != 0;
+    FPA_REQUIRE(!uniform || (d->gamma_stride == 0 && d->alpha_stride == 0),
+                "FPA_UNIFORM_PHYSICS needs broadcast gamma and alpha (stride 0)");
     if (d->n_points == 0) return FPA_OK;
 
     Yaman4Params p;
@@ -333,26 +430,36 @@ int yaman4_launch(const fpa_yaman4_desc* d, cudaStream_t st) {
     p.status       = d->status;
     p.z0           = d->z0;
     p.z_max        = d->z_max;
+    p.h            = (d->z_max - d->z0) / (double)d->n_steps;
     p.gamma_stride = (int)d->gamma_stride;
     p.alpha_stride = (int)d->alpha_stride;
     p.A0_stride    = (int)d->A0_stride;
     p.n_steps      = (int)d->n_steps;
     // save_every > n_steps never fires; clamp so the countdown fits an int
     p.save_every   = (int)(d->save_every > d->n_steps ? d->n_steps + 1 : d->save_every);
+    p.check        = (d->flags & FPA_CHECK_NAN) ? 1 : 0;
     p.n_saved      = fpa_n_saved(d->n_steps, d->save_every);
+    p.coef         = make_coef(uniform ? d->gamma_uniform : 0.0, uniform ? d->alpha_uniform : 0.0, p.h);
 
-    const int phase = d->z_grid ? kExplicitGrid
-                                : ((d->flags & FPA_PHASE_EXACT) ? kExactUniform : kRecurrence);
-    const bool check = (d->flags & FPA_CHECK_NAN) != 0;
-    cudaError_t e;
-#define FPA_DISPATCH(T, M)                                             \
-    (check ? launch_phase<T, M, true>(p, phase, st) : launch_phase<T, M, false>(p, phase, st))
-    if (trace && pmax)  e = FPA_DISPATCH(true, true);
-    else if (trace)     e = FPA_DISPATCH(true, false);
-    else if (pmax)      e = FPA_DISPATCH(false, true);
-    else                e = FPA_DISPATCH(false, false);
-#undef FPA_DISPATCH
-    if (e != cudaSuccess) return cuda_fail(e, "yaman4_rk4_kernel launch");
+    cudaError_t  e;
+    const int    threads = 128;
+    const long   blocks  = (long)((p.n_points + threads - 1) / threads);
+    if (d->z_grid) {
+        yaman4_exact_kernel<true><<<blocks, threads, 0, st>>>(p);
+        e = cudaGetLastError();
+    } else if (d->flags & FPA_PHASE_EXACT) {
+        yaman4_exact_kernel<false><<<blocks, threads, 0, st>>>(p);
+        e = cudaGetLastError();
+    } else if (trace && pmax) {
+        e = launch_fast<true, true>(p, uniform, st);
+    } else if (trace) {
+        e = launch_fast<true, false>(p, uniform, st);
+    } else if (pmax) {
+        e = launch_fast<false, true>(p, uniform, st);
+    } else {
+        e = launch_fast<false, false>(p, uniform, st);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "yaman4 kernel launch");
     return FPA_OK;
 }
 

@@ -1,0 +1,110 @@
+"""GPU: the N-wave kernel (csrc/nwave.cu) against the CPU statement of SURVEY App. C
+(oracle/nwave_oracle.py) and, at N = 4 with the fixed process table, against the reference model
+(golden B1 trace).  No reference exists for N > 4: parity there is to the oracle only."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _table_as_list(plan):
+    t = plan.table
+    return [(int(a), int(b), int(c), int(d)) for a, b, c, d in zip(t["k"], t["l"], t["m"], t["weight"])]
+
+
+def test_n4_fixed_table_reproduces_reference_trace(gpu, golden):
+    """beta = [0,0,0,dbeta] + the fixed 4-entry table == yaman_model (golden B1, main.py:27-96)."""
+    nw = gpu.nwave
+    plan = nw.four_wave_plan(golden["b1_omega"])
+    cfg = gpu.config.custom_simulation_config(z_max=1000.0, dz=0.1, save_every=10)
+    gamma, alpha = golden["b1_gamma_alpha"]
+    r = nw.run_nwave_simulation(cfg, plan, gamma=gamma, alpha=alpha, p_in=golden["b1_p_in"],
+                                beta=[0.0, 0.0, 0.0, golden["b1_dbeta"][1]], outputs=("trace", "end", "pmax"))
+    A, A_ref = r["A_trace"][0], golden["b1_A"]
+    assert np.array_equal(r["z"], golden["b1_z"]) and A.shape == A_ref.shape
+    assert rel_err(np.abs(A[-1]) ** 2, np.abs(A_ref[-1]) ** 2) < 1e-10
+    assert np.max(np.abs(A - A_ref)) / np.max(np.abs(A_ref)) < 1e-10
+    assert np.array_equal(r["A_end"][0], A[-1]) and r["status"][0] == -1
+    assert rel_err(r["Pmax"][0], (np.abs(A) ** 2).max(axis=0)) < 1e-15
+
+
+def test_n21_dual_pump_plan_vs_oracle(gpu, nw_oracle, golden):
+    """BASELINE config 2 (21 lines, pumps at +-5, signal/idler at +-1), shortened to 400 steps."""
+    nw, fp = gpu.nwave, gpu.frequency_plan
+    wc, wd = golden["b1_sym"][0], golden["b1_sym"][1]
+    plan = nw.uniform_comb_plan(wc, wd / 5.0, range(-10, 11))
+    assert plan.n_waves == 21 and plan.n_triplets == 2760
+    b2, b3, b4 = golden["b1_beta"]
+    disp = gpu.dispersion.DispersionParams(omega_ref=wc, beta2=b2, beta3=b3, beta4=b4)
+    beta = nw.beta_per_wave(plan, disp)
+    p_in = np.zeros(21)
+    p_in[[5, 15]] = 0.5
+    p_in[[9, 11]] = 1e-5
+    gamma, alpha = golden["b1_gamma_alpha"]
+    cfg = gpu.config.custom_simulation_config(z_max=40.0, dz=0.1, save_every=10)
+    r = nw.run_nwave_simulation(cfg, plan, gamma=gamma, alpha=alpha, p_in=p_in, beta=beta, outputs=("trace", "end"))
+    z_ref, A_ref = nw_oracle.march(np.sqrt(p_in).astype(complex), gamma, alpha, beta, _table_as_list(plan),
+                                   plan.row_ptr.tolist(), z_max=40.0, n_steps=400, save_every=10)
+    assert np.array_equal(r["z"], z_ref)
+    A = r["A_trace"][0]
+    assert A.shape == (41, 21)
+    assert np.max(np.abs(A - A_ref)) / np.max(np.abs(A_ref)) < 1e-11
+    seeded = p_in > 0
+    assert rel_err(np.abs(A[-1, seeded]) ** 2, np.abs(A_ref[-1, seeded]) ** 2) < 1e-10
+    # cascaded FWM populated lines that started empty
+    assert (np.abs(A[-1, ~seeded]) ** 2).max() > 1e-12
+    # through the reference-shaped integrator API as a registered RHS kind
+    rhs = nw.NWaveRHS(plan, beta, gamma, alpha)
+    z2, A2 = gpu.integrators.integrate_interval(rhs, 40.0, 0.1, np.sqrt(p_in).astype(complex), None, save_every=10)
+    assert np.array_equal(z2, z_ref) and np.array_equal(A2, A)
+
+
+def test_n64_comb_batch_vs_oracle(gpu, nw_oracle):
+    """BASELINE config 5 plan (64 lines, 100 GHz, beta2..beta4), 40 steps, a batch of 3 pump powers:
+    one CTA per scan point, each checked against the oracle."""
+    nw = gpu.nwave
+    w0 = 2 * np.pi * 299792458.0 / 1550e-9
+    plan = nw.uniform_comb_plan(w0, 2 * np.pi * 100e9, range(-32, 32))
+    assert plan.n_triplets == 84320 and plan.n_pairs() == 2076
+    disp = gpu.dispersion.DispersionParams(omega_ref=w0, beta2=-2.57e-29, beta3=3.30e-41, beta4=-1.63e-55)
+    beta = nw.beta_per_wave(plan, disp)
+    rng = np.random.default_rng(0)
+    base = np.full(64, 1e-12)
+    base[32 + 1] = 1e-6
+    phases = rng.uniform(0, 2 * np.pi, 64)
+    pumps = np.array([0.1, 0.5, 1.0])
+    A0 = np.empty((3, 64), dtype=complex)
+    for b, pw in enumerate(pumps):
+        p = base.copy()
+        p[[32 - 4, 32 + 4]] = pw
+        A0[b] = np.sqrt(p) * np.exp(1j * phases)
+    cfg = gpu.config.custom_simulation_config(z_max=4.0, dz=0.1, save_every=20)
+    r = nw.run_nwave_simulation(cfg, plan, gamma=11.5e-3, alpha=2e-4, A0=A0, beta=beta, outputs=("trace", "end", "pmax"))
+    assert r["A_trace"].shape == (3, 3, 64) and (r["status"] == -1).all()
+    table = _table_as_list(plan)
+    for b in range(3):
+        z_ref, A_ref = nw_oracle.march(A0[b], 11.5e-3, 2e-4, beta, table, plan.row_ptr.tolist(), z_max=4.0,
+                                       n_steps=40, save_every=20)
+        assert np.max(np.abs(r["A_trace"][b] - A_ref)) / np.max(np.abs(A_ref)) < 1e-12
+        assert rel_err(np.abs(r["A_end"][b]) ** 2, np.abs(A_ref[-1]) ** 2) < 1e-9
+    # per-point gamma: a batch equals the single runs, bit for bit
+    g = np.array([5e-3, 11.5e-3, 2e-2])
+    rb = nw.run_nwave_simulation(cfg, plan, gamma=g, alpha=2e-4, A0=A0, beta=beta, outputs=("end",))
+    for b in range(3):
+        one = nw.run_nwave_simulation(cfg, plan, gamma=g[b], alpha=2e-4, A0=A0[b:b + 1], beta=beta, outputs=("end",))
+        assert np.array_equal(one["A_end"][0], rb["A_end"][b])
+
+
+def test_nwave_invariants(gpu):
+    """alpha = 0: total power is conserved by the N-wave system (Manley-Rowe), here to RK4 accuracy."""
+    nw = gpu.nwave
+    w0 = 1.2e15
+    plan = nw.uniform_comb_plan(w0, 2 * np.pi * 200e9, range(-4, 5))
+    disp = gpu.dispersion.DispersionParams(omega_ref=w0, beta2=-5e-28)
+    p_in = np.array([0, 0, 0.3, 1e-4, 0, 0, 0.4, 0, 1e-6], dtype=float)
+    cfg = gpu.config.custom_simulation_config(z_max=100.0, dz=0.05, save_every=100)
+    r = nw.run_nwave_simulation(cfg, plan, gamma=0.02, alpha=0.0, p_in=p_in, dispersion=disp)
+    P = (np.abs(r["A_trace"][0]) ** 2).sum(axis=1)
+    assert np.ptp(P) < 1e-11 * P[0]
