@@ -383,7 +383,7 @@ __global__ void yaman4_rhs_kernel(int64_t B, const double* z, const double* A, c
 #define FPA_YAMAN4_THREADS 128
 #endif
 #ifndef FPA_YAMAN4_MIN_BLOCKS
-#define FPA_YAMAN4_MIN_BLOCKS 4
+#define FPA_YAMAN4_MIN_BLOCKS 3
 #endif
 constexpr int kFastThreads = FPA_YAMAN4_THREADS, kFastMinBlocks = FPA_YAMAN4_MIN_BLOCKS;
 

@@ -52,6 +52,16 @@ def main():
                 best = (int(m.group(1), 16), a)
         lo, hi = best
     loop = [(a, t) for a, t in ins if lo <= a <= hi]
+    # regions skipped by a predicated forward branch inside the loop are cold paths (phase re-sync
+    # every 32 steps, the non-finite slow check, the save block): leave them out of the hot count
+    cold = []
+    for a, t in loop:
+        m = re.match(r"@!?U?P\d+\s+BRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)", t)
+        if m and a < int(m.group(1), 16) <= hi:
+            cold.append((a, int(m.group(1), 16)))
+    n_all = len(loop)
+    loop = [(a, t) for a, t in loop if not any(c0 < a < c1 for c0, c1 in cold)]
+    print(f"cold regions skipped: {[(hex(a), hex(b)) for a, b in cold]} ({n_all - len(loop)} instructions)")
     mix = Counter()
     cycles = 0
     three = 0
