@@ -48,6 +48,9 @@ ALPHA = float(np.log(10) / 10 * 0.5 / 1000)
 P_IN = [0.1, 0.1, 1e-7, 1e-7]
 LAM_P2 = 1558e-9
 FLOPS_PER_POINT_STEP = 568.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the hot kernel on this workload, from the
+# committed ncu capture (cannot be measured outside a profiler): 8.62 MB + 8.98 MB
+NCU_DRAM_BYTES_PER_LAUNCH = 17.6e6
 
 
 def workload_axes(rank: int, world: int):
@@ -153,15 +156,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self) -> dict:
+    def stop(self, t0: float = 0.0, t1: float = float("inf")) -> dict:
+        """Summary of the samples taken inside [t0, t1] (the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, smax, power, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.15]
+        for r in inside:
             try:
                 sm.append(float(r[0])); smax.append(float(r[1])); power.append(float(r[2]))
             except (ValueError, IndexError):
@@ -250,21 +255,23 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs a few hundred ms to deliver its first sample
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    t_end = time.time()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -362,7 +369,8 @@ def run_ours(args) -> None:
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": None,
+                     "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/r1_ncu_yaman4_fast_kernel.csv)",
                      "kernel": "yaman4_fast_kernel<PMAX,UNIFORM>", "kernel_ms": kernel_ms,
                      "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
                      "flops_per_point_step": FLOPS_PER_POINT_STEP,
