@@ -47,6 +47,8 @@ extern "C" {
                                     * step: h_i = z_{i+1}-z_i, sincos at every RK4   *
                                     * abscissa, k_1..k_4 formed (slower; default is  *
                                     * the constant-h / phase-recurrence fast kernel) */
+#define FPA_NWAVE_TABLE (1u << 6)   /* N-wave: force the enumerated-triplet kernel even   *
+                                    * when grid_slot is given                          */
 #define FPA_UNIFORM_PHYSICS (1u << 5) /* gamma and alpha are the same for every point *
                                     * (stride 0) AND their values are given in       *
                                     * gamma_uniform / alpha_uniform: the kernel then  *
@@ -249,12 +251,21 @@ typedef struct fpa_nwave_desc {
     double*            A_end;        /* [B,N] or NULL                                      */
     double*            Pmax;         /* [B,N] or NULL                                      */
     int32_t*           status;       /* [B]                                                */
+    /* Integer-grid plans (uniform combs): grid_slot[j] = g_j - g_min for every wave, grid_span =
+     * g_max - g_min + 1 (<= 512).  When set (and FPA_NWAVE_TABLE is not), the integrator uses the
+     * O(span^2) convolution form of the same ODE instead of the enumerated table (csrc/nwave_comb.cu);
+     * triplets / row_ptr may then be NULL. */
+    const int32_t*     grid_slot;    /* [N] or NULL                                        */
+    int32_t            grid_span;
+    int32_t            reserved2;
 } fpa_nwave_desc;
 
 int fpa_nwave_rk4_batch_dev(const fpa_nwave_desc* d, void* stream);
 int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device);
 /* Algorithmic flops per point.step the N-wave kernel is credited with. */
 double fpa_nwave_flops_per_step(int32_t n_waves, int64_t n_triplets, int64_t n_pairs);
+/* Same for the convolution-form kernel (O(span^2) work: credited with what it executes). */
+double fpa_nwave_comb_flops_per_step(int32_t n_waves, int32_t grid_span);
 
 /* ------------------------------------------------ measurement helpers */
 /* DFMA micro-benchmark: dependent-chain-free FP64 FMA loop on every SM.  Returns the

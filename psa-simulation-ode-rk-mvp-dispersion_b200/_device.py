@@ -197,8 +197,10 @@ def enumerate_triplets(grid_index) -> tuple[np.ndarray, np.ndarray]:
 
 def nwave_batch(beta, gamma, alpha, A0, table, row_ptr, *, z0=0.0, z_max, n_steps, save_every=1,
                 trace=False, end=True, pmax=False, check_nan=True, n_points: Optional[int] = None,
-                device: Optional[int] = None) -> dict:
-    """B points of the N-wave model through `fpa_nwave_rk4_batch_host`."""
+                grid_index=None, force_table: bool = False, device: Optional[int] = None) -> dict:
+    """B points of the N-wave model through `fpa_nwave_rk4_batch_host`.  With `grid_index` (integer
+    grid position of every wave) the library integrates the convolution form of the same ODE
+    (O(span^2) per RHS) unless `force_table` asks for the enumerated-triplet kernel."""
     A0 = c128(A0)
     N = A0.shape[-1]
     beta = f64(beta)
@@ -227,9 +229,16 @@ def nwave_batch(beta, gamma, alpha, A0, table, row_ptr, *, z0=0.0, z_max, n_step
     d.A0, d.A0_stride = ptr(a0), a0s
     d.triplets, d.row_ptr, d.n_triplets = (ptr(table) if table.size else None), ptr(rows), table.size
     d.z0, d.z_max, d.n_steps, d.save_every = float(z0), float(z_max), n_steps, save_every
-    d.flags = _flags(trace, end, pmax, check_nan, False)
+    d.flags = _flags(trace, end, pmax, check_nan, False) | (_lib.NWAVE_TABLE if force_table else 0)
     d.A_trace, d.A_end, d.Pmax = ptr(out.get("A_trace")), ptr(out.get("A_end")), ptr(out.get("Pmax"))
     d.status = ptr(out["status"])
+    slots = None
+    if grid_index is not None:
+        g = np.asarray(grid_index, dtype=np.int64).reshape(-1)
+        if g.size != N:
+            raise ValueError("grid_index must hold one entry per wave")
+        slots = np.ascontiguousarray(g - g.min(), dtype=np.int32)
+        d.grid_slot, d.grid_span = ptr(slots), int(g.max() - g.min() + 1)
     dev = _lib.get_device() if device is None else int(device)
     _lib.check(_lib.lib().fpa_nwave_rk4_batch_host(C.byref(d), dev))
     return out

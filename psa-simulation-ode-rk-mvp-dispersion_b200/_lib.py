@@ -17,7 +17,7 @@ LIB_PATH = PKG_DIR / "libfpa_b200.so"
 
 # status codes / flags (include/fpa_b200.h)
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
-OUT_TRACE, OUT_END, OUT_PMAX, CHECK_NAN, PHASE_EXACT, UNIFORM_PHYSICS = 1, 2, 4, 8, 16, 32
+OUT_TRACE, OUT_END, OUT_PMAX, CHECK_NAN, PHASE_EXACT, UNIFORM_PHYSICS, NWAVE_TABLE = 1, 2, 4, 8, 16, 32, 64
 POINT_OK = -1
 PM_GENERAL_TAYLOR, PM_SYMMETRIC_EVEN, PM_PROVIDED = 0, 1, 2
 MAX_TAYLOR_ORDER = 12
@@ -94,6 +94,7 @@ class NwaveDesc(C.Structure):
         ("flags", C.c_uint32), ("reserved1", C.c_uint32),
         ("A_trace", C.c_void_p), ("A_end", C.c_void_p), ("Pmax", C.c_void_p),
         ("status", C.c_void_p),
+        ("grid_slot", C.c_void_p), ("grid_span", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -121,6 +122,7 @@ SIGNATURES = {
     "fpa_nwave_rk4_batch_dev": (C.c_int, [C.POINTER(NwaveDesc), C.c_void_p]),
     "fpa_nwave_rk4_batch_host": (C.c_int, [C.POINTER(NwaveDesc), C.c_int]),
     "fpa_nwave_flops_per_step": (C.c_double, [C.c_int32, C.c_int64, C.c_int64]),
+    "fpa_nwave_comb_flops_per_step": (C.c_double, [C.c_int32, C.c_int32]),
     "fpa_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp]),
     "fpa_yaman4_flops_per_step": (C.c_double, []),
     "fpa_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),

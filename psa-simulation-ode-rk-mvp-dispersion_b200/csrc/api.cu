@@ -28,6 +28,7 @@ int linear_launch(int64_t B, int dim, const double* y0, const double* lam, doubl
                   double* y_trace, double* y_end, int32_t* bad_scratch, int32_t* status,
                   cudaStream_t st);
 int nwave_launch(const fpa_nwave_desc* d, cudaStream_t st);
+int nwave_comb_launch(const fpa_nwave_desc* d, cudaStream_t st);
 int probe_run(int device, int iters, double* tflops, double* ms_out);
 
 // ----------------------------------------------------------------- error text (per host thread)
@@ -130,6 +131,33 @@ static int host_stream(int device, cudaStream_t* st) {
     }
     *st = it->second;
     return FPA_OK;
+}
+
+// ----------------------------------------------------------------- N-wave dispatch
+static bool nwave_use_comb(const fpa_nwave_desc* d) {
+    return d->grid_slot != nullptr && !(d->flags & FPA_NWAVE_TABLE);
+}
+
+static int nwave_dispatch(const fpa_nwave_desc* d, cudaStream_t st) {
+    if (!nwave_use_comb(d)) return nwave_launch(d, st);
+    FPA_REQUIRE(d->n_points >= 0 && d->n_points < 2147483647LL, "bad n_points");
+    FPA_REQUIRE(d->n_waves >= 1, "n_waves must be >= 1");
+    if (d->n_waves > 128 || d->grid_span > 512) {
+        set_error("comb kernel limits: n_waves <= 128, grid_span <= 512 (got %d, %d)", d->n_waves, d->grid_span);
+        return FPA_ERR_UNSUPPORTED;
+    }
+    FPA_REQUIRE(d->grid_span >= d->n_waves, "grid_span must cover all waves");
+    FPA_REQUIRE(d->n_steps >= 1 && d->n_steps < 2147483647LL, "n_steps must be in [1, 2^31)");
+    FPA_REQUIRE(d->save_every >= 1, "save_every must be a positive integer");
+    FPA_REQUIRE(d->beta && d->gamma && d->alpha && d->A0, "beta/gamma/alpha/A0 must be set");
+    FPA_REQUIRE((d->gamma_stride | 1) == 1 && (d->alpha_stride | 1) == 1 && (d->A0_stride | 1) == 1 &&
+                    (d->beta_stride | 1) == 1,
+                "strides must be 0 (broadcast) or 1 (per point)");
+    FPA_REQUIRE(!(d->flags & FPA_OUT_TRACE) || d->A_trace, "FPA_OUT_TRACE needs A_trace");
+    FPA_REQUIRE(!(d->flags & FPA_OUT_PMAX) || d->Pmax, "FPA_OUT_PMAX needs Pmax");
+    FPA_REQUIRE(!(d->flags & FPA_OUT_END) || d->A_end, "FPA_OUT_END needs A_end");
+    if (d->n_points == 0) return FPA_OK;
+    return nwave_comb_launch(d, st);
 }
 
 // ----------------------------------------------------------------- sweep (device pointers)
@@ -570,7 +598,7 @@ int fpa_nwave_rk4_batch_dev(const fpa_nwave_desc* d, void* stream) {
         set_error("no CUDA device is visible: libfpa_b200 has no CPU path");
         return FPA_ERR_NO_DEVICE;
     }
-    return nwave_launch(d, static_cast<cudaStream_t>(stream));
+    return nwave_dispatch(d, static_cast<cudaStream_t>(stream));
 }
 
 int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device) {
@@ -580,7 +608,8 @@ int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device) {
     FPA_REQUIRE(d->n_steps >= 1, "n_steps must be >= 1");
     FPA_REQUIRE(d->save_every >= 1, "save_every must be a positive integer");
     FPA_REQUIRE(d->beta && d->gamma && d->alpha && d->A0, "beta/gamma/alpha/A0 must be set");
-    FPA_REQUIRE(d->n_triplets >= 0 && d->row_ptr, "triplet table must be set");
+    const bool comb = nwave_use_comb(d);
+    FPA_REQUIRE(comb || (d->n_triplets >= 0 && d->row_ptr), "triplet table must be set");
     FPA_REQUIRE((d->gamma_stride | 1) == 1 && (d->alpha_stride | 1) == 1 && (d->A0_stride | 1) == 1 &&
                     (d->beta_stride | 1) == 1,
                 "strides must be 0 (broadcast) or 1 (per point)");
@@ -595,14 +624,15 @@ int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device) {
     const size_t ns = (size_t)fpa_n_saved(d->n_steps, d->save_every);
     const size_t n_b = (d->beta_stride ? B : 1) * N, n_g = d->gamma_stride ? B : 1;
     const size_t n_a = d->alpha_stride ? B : 1, n_A0 = (d->A0_stride ? B : 1) * N * 2;
-    const size_t n_t = (size_t)d->n_triplets, n_grid = 0;
+    const size_t n_t = comb ? 0 : (size_t)d->n_triplets, n_grid = 0;
     const size_t n_tr = trace ? B * ns * N * 2 : 0;
     void* ws = nullptr;
     FPA_TRY(workspace(device, 5,
                       Carver::need(n_b * 8) + Carver::need(n_g * 8) + Carver::need(n_a * 8) +
                           Carver::need(n_A0 * 8) + Carver::need(n_t * sizeof(fpa_triplet)) +
                           Carver::need((N + 1) * 8) + Carver::need(n_grid * 8) + Carver::need(n_tr * 8) +
-                          Carver::need(B * N * 16) + Carver::need(B * N * 8) + Carver::need(B * 4),
+                          Carver::need(B * N * 16) + Carver::need(B * N * 8) + Carver::need(B * 4) +
+                          Carver::need(N * 4),
                       &ws));
     cudaStream_t st;
     FPA_TRY(host_stream(device, &st));
@@ -618,12 +648,16 @@ int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device) {
     double*      Ae   = cv.take<double>(B * N * 2);
     double*      Pm   = cv.take<double>(B * N);
     int32_t*     stt  = cv.take<int32_t>(B);
+    int32_t*     slot = cv.take<int32_t>(N);
+    if (comb) FPA_TRY(up(slot, d->grid_slot, N * 4, st));
     FPA_TRY(up(beta, d->beta, n_b * 8, st));
     FPA_TRY(up(gam, d->gamma, n_g * 8, st));
     FPA_TRY(up(alp, d->alpha, n_a * 8, st));
     FPA_TRY(up(A0, d->A0, n_A0 * 8, st));
-    FPA_TRY(up(tab, d->triplets, n_t * sizeof(fpa_triplet), st));
-    FPA_TRY(up(rows, d->row_ptr, (N + 1) * 8, st));
+    if (!comb) {
+        FPA_TRY(up(tab, d->triplets, n_t * sizeof(fpa_triplet), st));
+        FPA_TRY(up(rows, d->row_ptr, (N + 1) * 8, st));
+    }
     fpa_nwave_desc dd = *d;
     dd.beta     = beta;
     dd.gamma    = gam;
@@ -635,8 +669,8 @@ int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device) {
     dd.A_end    = endo ? Ae : nullptr;
     dd.Pmax     = pmax ? Pm : nullptr;
     dd.status   = stt;
-    // the kernel reads row_ptr on the device but the launcher needs the host copy for sizing
-    FPA_TRY(nwave_launch(&dd, st));
+    dd.grid_slot = comb ? slot : nullptr;
+    FPA_TRY(nwave_dispatch(&dd, st));
     if (trace) FPA_TRY(down(d->A_trace, tr, n_tr * 8, st));
     if (endo) FPA_TRY(down(d->A_end, Ae, B * N * 16, st));
     if (pmax) FPA_TRY(down(d->Pmax, Pm, B * N * 8, st));

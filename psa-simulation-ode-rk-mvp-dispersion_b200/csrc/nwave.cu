@@ -32,6 +32,7 @@ struct NwaveParams {
     const int64_t*     row_ptr;
     int64_t            n_triplets;
     int                table_in_smem;
+    int                table_in_smem_only_one_cta;
     double             z0, z_max;
     int                n_steps, save_every;
     int64_t            n_saved;
@@ -312,9 +313,17 @@ int nwave_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     const size_t with_table = nwave_smem_bytes(d->n_waves, d->n_triplets);
     p.table_in_smem = with_table <= 200 * 1024 ? 1 : 0;
     const size_t smem = p.table_in_smem ? with_table : nwave_smem_bytes(d->n_waves, 0);
-    // small plans: one warp per point; large plans: 8 warps per point
-    const int64_t per_row = d->n_triplets / d->n_waves;
-    const int     threads = (d->n_waves <= 32 && per_row <= 256) ? 32 : 256;
+    p.table_in_smem_only_one_cta = smem > 100 * 1024 ? 1 : 0;
+    // Warps per point: one warp per row of the triplet sum (up to 32 warps) when the batch is too
+    // small to fill the GPU with points -- a single run (B = 1) is one CTA and its only parallelism
+    // is across rows and entries; for large batches 8 warps per point leave room for several CTAs
+    // per SM.
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int warps = d->n_waves < 32 ? d->n_waves : 32;
+    if (d->n_points >= 4 * (int64_t)sms && !p.table_in_smem_only_one_cta) warps = warps < 8 ? warps : 8;
+    const int threads = 32 * warps;
 
     cudaError_t e = cudaFuncSetAttribute(nwave_rk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);

@@ -45,7 +45,14 @@ class NWavePlan:
         key = self.table["k"].astype(np.int64) * 65536 + self.table["l"].astype(np.int64)
         return int(np.unique(key).size)
 
-    def flops_per_step(self) -> float:
+    @property
+    def grid_span(self) -> int:
+        return int(self.grid_index.max() - self.grid_index.min() + 1)
+
+    def flops_per_step(self, form: str = "table") -> float:
+        """Algorithmic flops per point.step credited to the kernel that runs (`table` | `comb`)."""
+        if form == "comb":
+            return float(_lib.lib().fpa_nwave_comb_flops_per_step(self.n_waves, self.grid_span))
         return float(_lib.lib().fpa_nwave_flops_per_step(self.n_waves, self.n_triplets, self.n_pairs()))
 
 
@@ -71,7 +78,7 @@ def four_wave_plan(omega: Sequence[float]) -> NWavePlan:
     entries, the all-equal-omega examples to every combination)."""
     table = np.array([(2, 3, 1, 2), (2, 3, 0, 2), (0, 1, 3, 2), (0, 1, 2, 2)], dtype=_lib.TRIPLET_DTYPE)
     rows = np.arange(5, dtype=np.int64)
-    return NWavePlan(omega=np.asarray(omega, dtype=float).reshape(4), grid_index=np.full(4, -1, np.int32),
+    return NWavePlan(omega=np.asarray(omega, dtype=float).reshape(4), grid_index=np.full(4, -1, np.int32),  # off-grid
                      table=table, row_ptr=rows, labels=("pump1", "pump2", "signal", "idler"))
 
 
@@ -87,13 +94,26 @@ def beta_per_wave(plan: NWavePlan, disp: DispersionParams, *, max_order: int = 4
     return np.asarray(beta_taylor(plan.omega, d, max_order=max_order), dtype=float)
 
 
+def _grid_or_none(plan: NWavePlan, form: str):
+    """grid indices to hand to the library: integer-grid plans use the convolution-form kernel
+    (`auto` / `comb`); `table` or an off-grid plan uses the enumerated triplets."""
+    if form not in ("auto", "comb", "table"):
+        raise ValueError("form must be 'auto', 'comb' or 'table'")
+    off_grid = bool(np.all(plan.grid_index < 0)) and plan.grid_index.size > 1 and \
+        plan.grid_index.min() == plan.grid_index.max()
+    if form == "comb" and off_grid:
+        raise ValueError("the convolution form needs an integer-grid plan")
+    return None if (form == "table" or off_grid) else plan.grid_index
+
+
 class NWaveRHS:
     """Registered device RHS kind for integrators.*: holds plan, per-wave beta, gamma, alpha
     (all in the length unit of z)."""
     fpa_kind = "nwave"
 
-    def __init__(self, plan: NWavePlan, beta, gamma: float, alpha: float = 0.0):
+    def __init__(self, plan: NWavePlan, beta, gamma: float, alpha: float = 0.0, form: str = "auto"):
         self.plan = plan
+        self.form = form
         self.beta = np.asarray(beta, dtype=float).reshape(plan.n_waves)
         self.gamma, self.alpha = float(gamma), float(alpha)
 
@@ -111,16 +131,19 @@ class NWaveRHS:
         return _device.nwave_batch(self.beta, self.gamma, self.alpha, y0, self.plan.table,
                                    self.plan.row_ptr, z0=z0, z_max=z_max, n_steps=n_steps,
                                    save_every=save_every, trace=trace, end=end, pmax=pmax,
-                                   check_nan=check_nan)
+                                   check_nan=check_nan, grid_index=_grid_or_none(self.plan, self.form),
+                                   force_table=self.form == "table")
 
 
 def run_nwave_simulation(cfg: SimulationConfig, plan: NWavePlan, *, gamma, alpha, p_in=None,
                          phase_in=None, A0=None, dispersion: Optional[DispersionParams] = None,
                          beta=None, max_order: int = 4, length_unit: str = "m",
-                         outputs: Sequence[str] = ("trace",), device: Optional[int] = None) -> dict:
+                         outputs: Sequence[str] = ("trace",), form: str = "auto",
+                         device: Optional[int] = None) -> dict:
     """B >= 1 N-wave runs in one launch.  Initial state from p_in/phase_in [N] or A0 [B,N];
     gamma / alpha scalars or [B]; per-wave beta from `dispersion` (per length_unit) or given
-    explicitly ([N] or [B,N]).  Returns dict(z, A_trace[B,n_saved,N], A_end, Pmax, status)."""
+    explicitly ([N] or [B,N]).  `form`: 'auto' (convolution form for integer-grid plans, else the
+    triplet table), 'comb', 'table'.  Returns dict(z, A_trace[B,n_saved,N], A_end, Pmax, status)."""
     validate_config(cfg)
     s = _length_scale_to_m(length_unit)
     N = plan.n_waves
@@ -143,7 +166,8 @@ def run_nwave_simulation(cfg: SimulationConfig, plan: NWavePlan, *, gamma, alpha
     r = _device.nwave_batch(beta, np.asarray(gamma, dtype=float) / s, np.asarray(alpha, dtype=float) / s,
                             A0.reshape(-1, N), plan.table, plan.row_ptr, z_max=z_max, n_steps=n_steps,
                             save_every=cfg.save_every, trace="trace" in want, end="end" in want,
-                            pmax="pmax" in want, check_nan=cfg.check_nan, device=device)
+                            pmax="pmax" in want, check_nan=cfg.check_nan, device=device,
+                            grid_index=_grid_or_none(plan, form), force_table=form == "table")
     grid = np.linspace(0.0, z_max, n_steps + 1)
     r["z"] = np.concatenate((grid[:1], grid[cfg.save_every::cfg.save_every])) / s
     r["n_steps"] = n_steps

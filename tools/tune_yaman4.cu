@@ -60,10 +60,11 @@ void report(Yaman4Params p, int sms, double peak_tf) {
     // tail-free batch: a whole number of waves
     const int64_t per_wave = (int64_t)sms * resident * THREADS;
     p.n_points = (full / per_wave) * per_wave;
+    if (p.n_points == 0) p.n_points = per_wave;
     const float  ms_even = time_variant<THREADS, MB>(p, 3);
     const double tf_full = 568.0 * full * p.n_steps / (ms_full * 1e-3) / 1e12;
     const double tf_even = 568.0 * p.n_points * p.n_steps / (ms_even * 1e-3) / 1e12;
-    printf("threads=%3d min_blocks=%d regs=%3d resident=%2d blocks (%2d warps/SMSP) | 1e6 pts: %7.3f ms %6.2f TF "
+    printf("threads=%3d min_blocks=%d regs=%3d resident=%2d blocks (%2d warps/SMSP) | full batch: %7.3f ms %6.2f TF "
            "(%4.1f%%) | %lld pts (whole waves): %7.3f ms %6.2f TF (%4.1f%%)\n",
            THREADS, MB, fa.numRegs, resident, resident * THREADS / 128, ms_full, tf_full, 100 * tf_full / peak_tf,
            (long long)p.n_points, ms_even, tf_even, 100 * tf_even / peak_tf);
@@ -74,8 +75,8 @@ int main(int argc, char** argv) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, 0);
     const int     sms = prop.multiProcessorCount;
-    const int64_t B = 1000000;
-    const int     n_steps = 2500;
+    const int64_t B = argc > 2 ? atoll(argv[2]) : 1000000;
+    const int     n_steps = argc > 3 ? atoi(argv[3]) : 2500;
     std::vector<double> dbeta(B);
     for (int64_t i = 0; i < B; ++i) dbeta[i] = -0.015 + 0.03 * (double)i / (double)B;
     const double consts[10] = {11.5e-3, 1.1512925464970228e-4, 0.31622776601683794, 0, 0.31622776601683794, 0,
