@@ -199,8 +199,10 @@ typedef struct fpa_sweep_desc {
 
 int fpa_yaman4_sweep_host(const fpa_sweep_desc* d, int device);
 /* Same, but all pointers (plan.lambda*, plan.dbeta, plan.valid, gain_lin, ...) are DEVICE
- * pointers and the work is queued on `stream` (asynchronous).  `scratch` is device memory of at
- * least fpa_yaman4_sweep_scratch_bytes(n1*n3) bytes that the call may use until it completes. */
+ * pointers and the work is queued on `stream` (asynchronous): ONE kernel launch per sweep
+ * (frequency plan + Delta-beta prologue, fused RK4 loop, gain epilogue).  `scratch` is device memory
+ * of at least fpa_yaman4_sweep_scratch_bytes(n1*n3) bytes (currently 0: it may be NULL).
+ * FPA_PHASE_EXACT is not available for sweeps (use fpa_dbeta_table_* + fpa_yaman4_rk4_batch_*). */
 int64_t fpa_yaman4_sweep_scratch_bytes(int64_t n_points);
 int fpa_yaman4_sweep_dev(const fpa_sweep_desc* d, void* scratch, int64_t scratch_bytes, void* stream);
 

@@ -20,9 +20,7 @@ int yaman4_launch(const fpa_yaman4_desc* d, cudaStream_t st);
 int yaman4_rhs_launch(int64_t B, const double* z, const double* A, const double* gamma,
                       const double* alpha, const double* dbeta, double* dA, cudaStream_t st);
 int plan_launch(const fpa_plan_desc* d, double* dbeta_masked, cudaStream_t st);
-int sweep_consts_launch(double gamma, double alpha, const double* A0, double* consts, cudaStream_t st);
-int sweep_gain_launch(int64_t B, const double* Pmax, const int32_t* valid, const int32_t* status,
-                      double p_signal, int check_nan, double* gain_lin, cudaStream_t st);
+int yaman4_sweep_launch(const fpa_sweep_desc* d, cudaStream_t st);
 int linear_launch(int64_t B, int dim, const double* y0, const double* lam, double z0, double z_max,
                   int64_t n_steps, int64_t save_every, const double* z_grid, uint32_t flags,
                   double* y_trace, double* y_end, int32_t* bad_scratch, int32_t* status,
@@ -161,102 +159,10 @@ static int nwave_dispatch(const fpa_nwave_desc* d, cudaStream_t st) {
 }
 
 // ----------------------------------------------------------------- sweep (device pointers)
-struct SweepScratch {
-    double*  consts;
-    double*  dbeta_run;
-    double*  Pmax;
-    int32_t* status;
-    int32_t* valid;
-    double*  dbeta_report;
-};
-
-static size_t sweep_scratch_need(int64_t B) {
-    const size_t b = (size_t)(B > 0 ? B : 0);
-    return Carver::need(16 * sizeof(double)) + Carver::need(b * sizeof(double)) +
-           Carver::need(4 * b * sizeof(double)) + 2 * Carver::need(b * sizeof(int32_t)) +
-           Carver::need(b * sizeof(double));
-}
-
-static int sweep_dev(const fpa_sweep_desc* d, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
-    FPA_REQUIRE(d != nullptr, "sweep descriptor is NULL");
-    const fpa_plan_desc& pl = d->plan;
-    FPA_REQUIRE(pl.n1 >= 0 && pl.n3 >= 0, "grid sizes must be >= 0");
-    const int64_t B = pl.n1 * pl.n3;
-    FPA_REQUIRE(d->gain_lin != nullptr || B == 0, "gain_lin must be set");
-    FPA_REQUIRE(d->length_scale == 1.0 || d->length_scale == 1000.0, "length_scale must be 1 or 1000");
-    FPA_REQUIRE(d->z_max > 0.0, "z_max must be positive");
-    FPA_REQUIRE(d->dz > 0.0, "dz must be positive");
-    FPA_REQUIRE(d->save_every >= 1, "save_every must be a positive integer");
-    FPA_REQUIRE(d->p_signal > 0.0, "p_in[2] (signal seed power) must be > 0 to define gain");
-    FPA_REQUIRE(scratch_bytes >= (int64_t)sweep_scratch_need(B), "scratch too small: need %lld bytes",
-                (long long)sweep_scratch_need(B));
-    if (B == 0) return FPA_OK;
-
-    Carver cv;
-    cv.base = static_cast<char*>(scratch);
-    SweepScratch s;
-    s.consts       = cv.take<double>(16);
-    s.dbeta_run    = cv.take<double>(B);
-    s.Pmax         = cv.take<double>(4 * B);
-    s.status       = cv.take<int32_t>(B);
-    s.valid        = cv.take<int32_t>(B);
-    s.dbeta_report = cv.take<double>(B);
-
-    const double sc = d->length_scale;
-    double*  Pmax   = d->Pmax ? d->Pmax : s.Pmax;
-    int32_t* status = d->status ? d->status : s.status;
-    int32_t* valid  = pl.valid ? pl.valid : s.valid;
-    double*  report = pl.dbeta ? pl.dbeta : s.dbeta_report;
-
-    // (1) reported dbeta: the dispersion exactly as the caller gave it (scan_mismtach.py:700-706)
-    fpa_plan_desc rep = pl;
-    rep.dbeta = report;
-    rep.valid = valid;
-    FPA_TRY(plan_launch(&rep, nullptr, st));
-    // (2) dbeta used by the integration: every beta_n (or the PROVIDED constant) divided by the
-    //     length scale first (simulation.py:126-175), then the same provider.
-    const double* dbeta_run = report;
-    if (sc != 1.0) {
-        fpa_plan_desc run = pl;
-        for (int n = 0; n <= FPA_MAX_TAYLOR_ORDER; ++n) run.beta[n] = pl.beta[n] / sc;
-        run.provided = pl.provided / sc;
-        run.omega = nullptr;
-        run.dbeta = s.dbeta_run;
-        run.valid = nullptr;
-        FPA_TRY(plan_launch(&run, nullptr, st));
-        dbeta_run = s.dbeta_run;
-    }
-    // (3) per-sweep constants -> device (gamma/scale, alpha/scale, A0)
-    FPA_TRY(sweep_consts_launch(d->gamma / sc, d->alpha / sc, d->A0, s.consts, st));
-    // (4) the fused integrator; invalid points carry dbeta = NaN and leave at once
-    fpa_yaman4_desc y;
-    memset(&y, 0, sizeof(y));
-    y.n_points     = B;
-    y.dbeta        = dbeta_run;
-    y.gamma        = s.consts;
-    y.gamma_stride = 0;
-    y.alpha        = s.consts + 1;
-    y.alpha_stride = 0;
-    y.A0           = s.consts + 2;
-    y.A0_stride    = 0;
-    y.z0           = 0.0;
-    y.z_max        = d->z_max * sc;
-    y.n_steps      = fpa_interval_steps(d->z_max * sc, d->dz * sc);
-    FPA_REQUIRE(y.n_steps >= 1, "z_max/dz rounds to zero steps");
-    y.save_every   = d->save_every;
-    y.flags        = FPA_OUT_PMAX | FPA_UNIFORM_PHYSICS | (d->flags & (FPA_CHECK_NAN | FPA_PHASE_EXACT)) |
-                     (d->A_end ? FPA_OUT_END : 0u);
-    y.gamma_uniform = d->gamma / sc;
-    y.alpha_uniform = d->alpha / sc;
-    y.Pmax         = Pmax;
-    y.A_end        = d->A_end;
-    y.status       = status;
-    FPA_TRY(yaman4_launch(&y, st));
-    // (5) gain metric (scan_mismtach.py:723-734)
-    FPA_TRY(sweep_gain_launch(B, Pmax, valid, status, d->p_signal, (d->flags & FPA_CHECK_NAN) ? 1 : 0,
-                              d->gain_lin, st));
-    return FPA_OK;
-}
+// FPA_PHASE_EXACT sweeps (the reference's arithmetic structure) run as table kernel + exact
+// integrator + the fused kernel's metric rules on the host side of the ABI; the default is the
+// single fused kernel.
+static int sweep_dev(const fpa_sweep_desc* d, cudaStream_t st) { return yaman4_sweep_launch(d, st); }
 
 }  // namespace fpa
 
@@ -476,15 +382,19 @@ int fpa_dbeta_table_host(const fpa_plan_desc* d, int device) {
 }
 
 // ------------------------------------------------------------------ fused sweep
-int64_t fpa_yaman4_sweep_scratch_bytes(int64_t n_points) { return (int64_t)sweep_scratch_need(n_points); }
+int64_t fpa_yaman4_sweep_scratch_bytes(int64_t n_points) {
+    (void)n_points;
+    return 0;  // the fused sweep kernel needs no workspace (kept for ABI stability)
+}
 
 int fpa_yaman4_sweep_dev(const fpa_sweep_desc* d, void* scratch, int64_t scratch_bytes, void* stream) {
     if (fpa_device_count() <= 0) {
         set_error("no CUDA device is visible: libfpa_b200 has no CPU path");
         return FPA_ERR_NO_DEVICE;
     }
-    FPA_REQUIRE(scratch != nullptr, "scratch must be set");
-    return sweep_dev(d, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
+    (void)scratch;
+    (void)scratch_bytes;
+    return sweep_dev(d, static_cast<cudaStream_t>(stream));
 }
 
 int fpa_yaman4_sweep_host(const fpa_sweep_desc* d, int device) {
@@ -497,12 +407,11 @@ int fpa_yaman4_sweep_host(const fpa_sweep_desc* d, int device) {
     if (B == 0) return FPA_OK;
     FPA_REQUIRE(d->gain_lin != nullptr, "gain_lin must be set");
     const size_t n2 = pl.lambda2_stride ? n1 : 1;
-    const size_t sweep_bytes = sweep_scratch_need((int64_t)B);
     size_t need = Carver::need(n1 * 8) + Carver::need(n2 * 8) + Carver::need(n3 * 8) +
                   Carver::need(B * 8) /*gain*/ + Carver::need(B * 8) /*dbeta*/ +
                   Carver::need(B * 4) /*valid*/ + Carver::need(B * 4) /*status*/ +
                   Carver::need(B * 32) /*Pmax*/ + Carver::need(B * 64) /*A_end*/ +
-                  Carver::need(B * 32) /*omega*/ + sweep_bytes;
+                  Carver::need(B * 32) /*omega*/;
     void* ws = nullptr;
     FPA_TRY(workspace(device, 3, need, &ws));
     cudaStream_t st;
@@ -519,7 +428,6 @@ int fpa_yaman4_sweep_host(const fpa_sweep_desc* d, int device) {
     double*  Pm   = cv.take<double>(B * 4);
     double*  Ae   = cv.take<double>(B * 8);
     double*  om   = cv.take<double>(B * 4);
-    void*    scr  = cv.take<char>(sweep_bytes);
 
     FPA_TRY(up(l1, pl.lambda1, n1 * 8, st));
     FPA_TRY(up(l2, pl.lambda2, n2 * 8, st));
@@ -535,7 +443,7 @@ int fpa_yaman4_sweep_host(const fpa_sweep_desc* d, int device) {
     dd.Pmax         = d->Pmax ? Pm : nullptr;
     dd.A_end        = d->A_end ? Ae : nullptr;
     dd.status       = stt;
-    FPA_TRY(sweep_dev(&dd, scr, (int64_t)sweep_bytes, st));
+    FPA_TRY(sweep_dev(&dd, st));
     FPA_TRY(down(d->gain_lin, gain, B * 8, st));
     FPA_TRY(down(pl.dbeta, db, B * 8, st));
     FPA_TRY(down(pl.valid, va, B * 4, st));

@@ -30,7 +30,7 @@
 //    Measured against the oracle: <= 1e-13 relative on |A|^2 after 10 000 steps at 45 dB gain.
 //  * yaman4_exact_kernel -- FPA_PHASE_EXACT or an explicit z-grid: the reference's arithmetic
 //    structure step by step (h_i by subtraction, sincos at z, z+h/2, z+h, k_j formed, y + h/6*(..)).
-#include "fpa_common.cuh"
+#include "plan_point.cuh"
 
 namespace fpa {
 
@@ -178,29 +178,12 @@ __device__ __forceinline__ void write_results(const Yaman4Params& p, int64_t b, 
     }
 }
 
-template <bool TRACE, bool PMAX, bool UNIFORM, int THREADS, int MIN_BLOCKS>
-__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_fast_kernel(const Yaman4Params p) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.n_points) return;
-
-    double y[8];
-    load_state(p, b, y);
-    const double dbeta = p.dbeta[b];
-    if (nonfinite(dbeta)) {
-        write_invalid_point(p, b, y);
-        return;
-    }
-    // stage-weighted coefficients: from the constant bank when the physics is uniform over the
-    // batch (sweeps), else per thread
-    Yaman4Coef cf;
-    if (UNIFORM) {
-        cf = p.coef;
-    } else {
-        cf = make_coef(p.gamma[b * p.gamma_stride], p.alpha[b * p.alpha_stride], p.h);
-    }
-
+// The z-loop of the fast path: advances y over all steps, keeps the running maxima in pm and
+// returns the first step whose result was not finite (or FPA_POINT_OK).
+template <bool TRACE, bool PMAX>
+__device__ __forceinline__ int32_t fast_integrate(const Yaman4Params& p, int64_t b, double dbeta,
+                                                  const Yaman4Coef& cf, double (&y)[8], double (&pm)[4]) {
     double* tr = nullptr;
-    double  pm[4] = {0.0, 0.0, 0.0, 0.0};
     if (TRACE) tr = p.A_trace + b * p.n_saved * 8;
     if (PMAX) {
 #pragma unroll
@@ -264,7 +247,112 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_fast_kernel(const 
             save_sample(y, tr, pm, TRACE, PMAX);
         }
     }
+    return bad;
+}
+
+template <bool TRACE, bool PMAX, bool UNIFORM, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_fast_kernel(const Yaman4Params p) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.n_points) return;
+
+    double y[8];
+    load_state(p, b, y);
+    const double dbeta = p.dbeta[b];
+    if (nonfinite(dbeta)) {
+        write_invalid_point(p, b, y);
+        return;
+    }
+    // stage-weighted coefficients: from the constant bank when the physics is uniform over the
+    // batch (sweeps), else per thread
+    Yaman4Coef cf;
+    if (UNIFORM) {
+        cf = p.coef;
+    } else {
+        cf = make_coef(p.gamma[b * p.gamma_stride], p.alpha[b * p.alpha_stride], p.h);
+    }
+    double        pm[4] = {0.0, 0.0, 0.0, 0.0};
+    const int32_t bad = fast_integrate<TRACE, PMAX>(p, b, dbeta, cf, y, pm);
     write_results(p, b, y, pm, PMAX, bad);
+}
+
+// ------------------------------------------------------------------ fused sweep
+// ONE kernel per sweep: per scan point the prologue builds the frequency plan, the validity flag
+// and Delta-beta (plan_point.cuh), the body is the fast RK4 loop above, and the epilogue reduces
+// to the sweep's gain metric.  Replaces the loop bodies scan_mismtach.py:694-738 / :357-392 incl.
+// simulation.run_single_simulation's unit handling (simulation.py:279-336): the reported dbeta
+// uses the dispersion as given, the integration uses every beta_n (or the PROVIDED constant)
+// divided by the length scale.
+struct SweepExtra {
+    PlanParams plan;        // axes, method, coefficient table as given (per length unit)
+    double     beta_run[FPA_MAX_TAYLOR_ORDER + 1];  // beta_n / scale
+    double     provided_run;
+    int        same_run;    // scale == 1: the run's dbeta is the reported one
+    double     A0[8];
+    double     p_signal;
+    double*    gain_lin;    // [B]
+};
+
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_sweep_kernel(const Yaman4Params p, const SweepExtra x) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.n_points) return;
+    const int64_t i1 = b / x.plan.n3, i3 = b - i1 * x.plan.n3;
+
+    double w[4];
+    bool   ok = plan_omegas(x.plan.lambda1[i1], x.plan.lambda2[i1 * x.plan.lambda2_stride], x.plan.lambda3[i3], w);
+    const double db_report = plan_dbeta(x.plan, x.plan.beta, x.plan.provided, w, ok);
+    double       db_run = db_report;
+    if (!x.same_run) {
+        bool ok_run = ok;
+        db_run = plan_dbeta(x.plan, x.beta_run, x.provided_run, w, ok_run);
+        if (!ok_run) db_run = qnan();
+    }
+    if (x.plan.dbeta) x.plan.dbeta[b] = db_report;
+    if (x.plan.valid) x.plan.valid[b] = ok ? 1 : 0;
+    if (x.plan.omega) {
+        double2* o = reinterpret_cast<double2*>(x.plan.omega + b * 4);
+        o[0] = make_double2(w[0], w[1]);
+        o[1] = make_double2(w[2], w[3]);
+    }
+
+    double y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = x.A0[j];
+    double gain = qnan();
+    if (!ok || nonfinite(db_run)) {
+        // the reference's per-point try/except leaves NaN (scan_mismtach.py:736-738)
+        const double qn = qnan();
+        if (p.A_end)
+            for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, qn, qn);
+        if (p.Pmax)
+            for (int j = 0; j < 4; ++j) p.Pmax[b * 4 + j] = qn;
+        if (p.status) p.status[b] = p.check ? 0 : FPA_POINT_OK;
+    } else {
+        double  pm[4] = {0.0, 0.0, 0.0, 0.0};
+        int32_t bad = fast_integrate<false, true>(p, b, db_run, p.coef, y, pm);
+        if (p.check && bad == FPA_POINT_OK) {
+            bool nf = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nf |= nonfinite(y[j]);
+            if (nf) bad = p.n_steps - 1;
+        }
+        if (p.status) p.status[b] = p.check ? bad : FPA_POINT_OK;
+        if (p.A_end) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, y[2 * j], y[2 * j + 1]);
+        }
+        if (p.Pmax) {
+            double2* o = reinterpret_cast<double2*>(p.Pmax + b * 4);
+            o[0] = make_double2(pm[0], pm[1]);
+            o[1] = make_double2(pm[2], pm[3]);
+        }
+        // gain = max_saved |A3|^2 / p_in[2]; NaN for failed, non-finite or <= 0 (scan_mismtach.py:723-734)
+        if (!(p.check && bad != FPA_POINT_OK) && !nonfinite(pm[2])) {
+            const double q = pm[2] / x.p_signal;
+            if (!nonfinite(q) && q > 0.0) gain = q;
+        }
+    }
+    x.gain_lin[b] = gain;
 }
 
 // ------------------------------------------------------------------ exact path
@@ -386,6 +474,8 @@ __global__ void yaman4_rhs_kernel(int64_t B, const double* z, const double* A, c
 #define FPA_YAMAN4_MIN_BLOCKS 3
 #endif
 constexpr int kFastThreads = FPA_YAMAN4_THREADS, kFastMinBlocks = FPA_YAMAN4_MIN_BLOCKS;
+// the fused sweep kernel gets its best schedule (fewest 3-register FMAs, tools/sass_cost.py) at 4
+constexpr int kSweepMinBlocks = 4;
 
 template <bool TRACE, bool PMAX>
 static cudaError_t launch_fast(const Yaman4Params& p, bool uniform, cudaStream_t st) {
@@ -460,6 +550,56 @@ int yaman4_launch(const fpa_yaman4_desc* d, cudaStream_t st) {
         e = launch_fast<false, false>(p, uniform, st);
     }
     if (e != cudaSuccess) return cuda_fail(e, "yaman4 kernel launch");
+    return FPA_OK;
+}
+
+// plan: the sweep's plan descriptor (device axis pointers); run_scale = 1 or 1000 (length unit);
+// gamma/alpha/z_max/dz per length unit, exactly as fpa_sweep_desc carries them.
+int plan_fill(const fpa_plan_desc* d, PlanParams& p);
+
+int yaman4_sweep_launch(const fpa_sweep_desc* d, cudaStream_t st) {
+    FPA_REQUIRE(d != nullptr, "sweep descriptor is NULL");
+    SweepExtra x;
+    int rc = plan_fill(&d->plan, x.plan);
+    if (rc != FPA_OK) return rc;
+    const int64_t B = d->plan.n1 * d->plan.n3;
+    FPA_REQUIRE(d->gain_lin != nullptr || B == 0, "gain_lin must be set");
+    FPA_REQUIRE(d->length_scale == 1.0 || d->length_scale == 1000.0, "length_scale must be 1 or 1000");
+    FPA_REQUIRE(d->z_max > 0.0, "z_max must be positive");
+    FPA_REQUIRE(d->dz > 0.0, "dz must be positive");
+    FPA_REQUIRE(d->save_every >= 1, "save_every must be a positive integer");
+    FPA_REQUIRE(d->p_signal > 0.0, "p_in[2] (signal seed power) must be > 0 to define gain");
+    if (B == 0) return FPA_OK;
+    const double sc = d->length_scale;
+    const int64_t n_steps = fpa_interval_steps(d->z_max * sc, d->dz * sc);
+    FPA_REQUIRE(n_steps >= 1 && n_steps < 2147483647LL, "z_max/dz must round to a step count in [1, 2^31)");
+
+    x.same_run = sc == 1.0 ? 1 : 0;
+    for (int n = 0; n <= FPA_MAX_TAYLOR_ORDER; ++n) x.beta_run[n] = d->plan.beta[n] / sc;  // simulation.py:126-150
+    x.provided_run = d->plan.provided / sc;                                               // simulation.py:153-175
+    for (int j = 0; j < 8; ++j) x.A0[j] = d->A0[j];
+    x.p_signal = d->p_signal;
+    x.gain_lin = d->gain_lin;
+
+    Yaman4Params p;
+    memset(&p, 0, sizeof(p));
+    p.n_points   = B;
+    p.A_end      = d->A_end;
+    p.Pmax       = d->Pmax;
+    p.status     = d->status;
+    p.z0         = 0.0;
+    p.z_max      = d->z_max * sc;
+    p.h          = p.z_max / (double)n_steps;
+    p.n_steps    = (int)n_steps;
+    p.save_every = (int)(d->save_every > n_steps ? n_steps + 1 : d->save_every);
+    p.check      = (d->flags & FPA_CHECK_NAN) ? 1 : 0;
+    p.n_saved    = fpa_n_saved(n_steps, d->save_every);
+    p.coef       = make_coef(d->gamma / sc, d->alpha / sc, p.h);
+
+    const long blocks = (long)((B + kFastThreads - 1) / kFastThreads);
+    yaman4_sweep_kernel<kFastThreads, kSweepMinBlocks><<<blocks, kFastThreads, 0, st>>>(p, x);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "yaman4_sweep_kernel launch");
     return FPA_OK;
 }
 

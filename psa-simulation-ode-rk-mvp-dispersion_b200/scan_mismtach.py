@@ -9,9 +9,9 @@ Public functions keep the reference's keyword signatures and return tuples:
 
 The reference runs `plan_from_wavelengths` + `compute_phase_mismatch` + `run_single_simulation`
 per point in a Python loop (:357-392, :694-738).  Here only the wavelength axes go to the GPU:
-`fpa_yaman4_sweep_host` builds the frequency plan, validity mask and Delta-beta table, integrates
-every point in one fused kernel and reduces to max_saved |A3|^2 / p_in[2]; gain / dbeta / status
-come back.  Per-point failures become NaN exactly where the reference's `except Exception`
+`fpa_yaman4_sweep_host` runs ONE kernel that builds each point's frequency plan, validity flag and
+Delta-beta, integrates it with the fused RK4 loop and reduces to max_saved |A3|^2 / p_in[2];
+gain / dbeta / status come back.  Per-point failures become NaN exactly where the reference's `except Exception`
 leaves NaN; argument errors raised before the reference's loop are raised here too.
 
 `sweep_gain_2d` extends the same call to a pump x signal wavelength grid (BASELINE config 4).
@@ -113,7 +113,7 @@ def _run_constants_ok(cfg, gamma, alpha, dispersion, pm_cfg, length_unit) -> boo
 def sweep_gain_2d(*, cfg: SimulationConfig, lambda_p1_m, lambda_p2_m, lambda_signal_m, gamma: float,
                   alpha: float, p_in, phase_in=None, dispersion: Optional[DispersionParams] = None,
                   phase_matching_cfg: Optional[PhaseMatchingConfig] = None, length_unit: str = "m",
-                  gain_unit: str = "dB", phase_exact: bool = False, want_pmax: bool = False,
+                  gain_unit: str = "dB", want_pmax: bool = False,
                   device: Optional[int] = None, out: Optional[dict] = None) -> dict:
     """max-over-saved signal gain and dbeta on the grid lambda_p1[n1] x lambda_signal[n3]
     (lambda_p2 scalar or [n1]).  Returns dict(gain[n1,n3] in gain_unit, gain_lin, dbeta, valid,
@@ -158,7 +158,7 @@ def sweep_gain_2d(*, cfg: SimulationConfig, lambda_p1_m, lambda_p2_m, lambda_sig
     d.z_max, d.dz = float(cfg.z_max), float(cfg.dz)
     d.length_scale = s
     d.save_every = int(cfg.save_every)
-    d.flags = (_lib.CHECK_NAN if cfg.check_nan else 0) | (_lib.PHASE_EXACT if phase_exact else 0)
+    d.flags = _lib.CHECK_NAN if cfg.check_nan else 0
     out = _device.sweep(d, want_pmax=want_pmax, device=device, out=out)
     g = out["gain_lin"]
     with np.errstate(invalid="ignore", divide="ignore"):

@@ -58,12 +58,12 @@ def build_source(orders):
 def score(orders, tag):
     src = WORK / f"cand_{tag}.cu"
     cub = WORK / f"cand_{tag}.cubin"
-    body = build_source(orders).replace('#include "fpa_common.cuh"',
-                                        f'#include "{SRC.parent}/fpa_common.cuh"')
+    body = build_source(orders).replace('#include "plan_point.cuh"',
+                                        f'#include "{SRC.parent}/plan_point.cuh"')
     body += ("\nnamespace fpa { template __global__ void yaman4_fast_kernel<false, true, true, 128, 3>"
              "(const Yaman4Params); }\n")
     # keep only the one instantiation: drop the launcher section (it instantiates everything)
-    cut = body.index("// RHS-only kernel")
+    cut = body.index("// ------------------------------------------------------------------ fused sweep")
     tail = body.index("}  // namespace fpa", cut)
     body = body[:cut] + body[tail:]
     src.write_text(body)

@@ -22,6 +22,10 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 }  // namespace fpa
 extern "C" int64_t fpa_n_saved(int64_t n, int64_t s) { return n / s + 1; }
+extern "C" int64_t fpa_interval_steps(double z_max, double dz) { return (int64_t)nearbyint(z_max / dz); }
+namespace fpa {
+int plan_fill(const fpa_plan_desc*, PlanParams&) { return FPA_ERR_UNSUPPORTED; }  // sweeps are not tuned here
+}
 
 using namespace fpa;
 
