@@ -48,9 +48,10 @@ ALPHA = float(np.log(10) / 10 * 0.5 / 1000)
 P_IN = [0.1, 0.1, 1e-7, 1e-7]
 LAM_P2 = 1558e-9
 FLOPS_PER_POINT_STEP = 568.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the hot kernel on this workload, from the
-# committed ncu capture (cannot be measured outside a profiler): 8.62 MB + 8.98 MB
-NCU_DRAM_BYTES_PER_LAUNCH = 17.6e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused sweep kernel on this workload,
+# from the committed ncu capture (cannot be measured outside a profiler): 109.8 KB read + 2.0 KB written --
+# the 24 MB of per-point results are still in the 126 MB L2 when the kernel ends
+NCU_DRAM_BYTES_PER_LAUNCH = 111872.0
 
 
 def workload_axes(rank: int, world: int):
@@ -370,7 +371,7 @@ def run_ours(args) -> None:
         "clocks": clocks,
         "roofline": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/r1_ncu_yaman4_fast_kernel.csv)",
+                     "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/r1_ncu_yaman4_sweep_kernel.csv)",
                      "kernel": "yaman4_fast_kernel<PMAX,UNIFORM> (the z-loop the fused yaman4_sweep_kernel runs)", "kernel_ms": kernel_ms,
                      "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
                      "flops_per_point_step": FLOPS_PER_POINT_STEP,
