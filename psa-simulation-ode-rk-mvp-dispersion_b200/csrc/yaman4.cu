@@ -200,7 +200,13 @@ __device__ __forceinline__ int32_t fast_integrate(const Yaman4Params& p, int64_t
     double  qr = cf.q0, qi = 0.0;  // (h/2)*2*gamma*exp(i*dbeta*z_i)
     int     save_ctr = p.save_every;
     int32_t bad = FPA_POINT_OK;
-    const double third = 1.0 / 3.0, two_thirds = 2.0 / 3.0;
+    // Weights of the stage states in y' = -y/3 + ys2/3 + 2 ys3/3 + ys4/3 + (h/6) f(ys4).  They must sum
+    // to EXACTLY one in floating point: fl(1/3) + fl(2/3) = 1 - 2^-54 shrinks |A| by that factor every
+    // step (and fl(1/3) + fl(1 - fl(1/3)) = 1 + 2^-54 grows it), and the Kerr phase integrates the
+    // amplitude error -- quadratic growth, 3e-10 rad after 2e5 steps (tests/test_gpu_edges.py).  The y and
+    // ys2 weights cancel exactly (same constant); 1 - fl(2/3) is exactly representable, so the ys4 weight
+    // third_c = 1 - fl(2/3) makes two_thirds + third_c == 1 with no rounding.
+    const double third = 1.0 / 3.0, two_thirds = 2.0 / 3.0, third_c = 1.0 - two_thirds;
 
     for (int i = 0; i < n_steps; ++i) {
         if ((i & (kResync - 1)) == 0) {
@@ -235,7 +241,7 @@ __device__ __forceinline__ int32_t fast_integrate(const Yaman4Params& p, int64_t
         // stage 3: ys = y + h f(z+h/2, yt)
         stage(yt, y, q2r, q2i, cf.cg[1], cf.c2g[1], cf.cn[1], ys, Sx);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fma(third, ys[j], acc[j]);
+        for (int j = 0; j < 8; ++j) acc[j] = fma(third_c, ys[j], acc[j]);
         // stage 4: y' = acc + (h/6) f(z+h, ys)
         stage(ys, acc, q6r, q6i, cf.cg[2], cf.c2g[2], cf.cn[2], y, Sx);
 

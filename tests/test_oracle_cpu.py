@@ -183,3 +183,31 @@ def test_triplet_enumeration_known_counts(nw_oracle):
     assert len(table) == 2760 and NW.count_ordered(range(-10, 11)) == (6181, 5320, 227)
     per_row = np.diff(rows)
     assert per_row.min() >= 100 and per_row.max() <= 150
+
+
+def test_fast_kernel_algorithm_model_vs_oracle(oracle):
+    """CPU model of the fast kernel's arithmetic (oracle/fast_kernel_model.py: constant step, stage
+    states written directly, rebuilt RK4 combination, phase recurrence) against the reference's
+    arithmetic: <= 1e-13 after 3000 steps; with the naive weights fl(1/3), fl(2/3), fl(1/3) (sum
+    1 - 2^-54) the systematic amplitude drift is an order of magnitude larger."""
+    from oracle import fast_kernel_model as M
+    from fractions import Fraction as F
+    t, tt, tc = M.weights("shipped")
+    assert F(tt) + F(tc) == 1 and t == 1.0 / 3.0                  # exact rational arithmetic
+    assert F(M.weights("naive")[1]) + F(M.weights("naive")[2]) == 1 - F(1, 2 ** 54)
+    A0 = oracle.initial_amplitudes([0.5, 0.5, 1e-8, 1e-8])
+    g, a, db, zmax, n = 11.5e-3, 2e-4, 4e-4, 30.0, 3000
+    z, A = oracle.march_interval(oracle.yaman_rhs_p, zmax, zmax / n, A0, oracle.YamanPoint(g, a, db), save_every=n)
+    ref = A[-1]
+    good = M.integrate(A0, g, a, db, zmax, n)[-1]
+    bad = M.integrate(A0, g, a, db, zmax, n, weight_kind="naive")[-1]
+    err = lambda y: float(np.max(np.abs(np.abs(y[:2]) ** 2 - np.abs(ref[:2]) ** 2) / np.abs(ref[:2]) ** 2))  # noqa: E731
+    assert err(good) < 5e-14
+    assert err(bad) > 5 * err(good) and err(bad) > 2e-13
+    assert np.max(np.abs(good - ref)) / np.max(np.abs(ref)) < 1e-13
+    # a stronger-coupling, lossless case with save points (config-3 physics, metres)
+    A0 = oracle.initial_amplitudes([0.1, 0.1, 1e-5, 0.0])
+    z, A = oracle.march_interval(oracle.yaman_rhs_p, 500.0, 1.0, A0, oracle.YamanPoint(0.01, 0.0, -0.013), save_every=100)
+    S = M.integrate(A0, 0.01, 0.0, -0.013, 500.0, 500, save_every=100)
+    assert len(S) == len(A)
+    assert np.max(np.abs(np.array(S) - A)) / np.max(np.abs(A)) < 1e-13
