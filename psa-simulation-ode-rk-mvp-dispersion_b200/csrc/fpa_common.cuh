@@ -48,4 +48,10 @@ __device__ __forceinline__ void store_c128(double* p, double re, double im) {
     *reinterpret_cast<double2*>(p) = make_double2(re, im);
 }
 
+// 32-byte store of two complex128 (sm_100 256-bit vector store: one full 32 B sector per thread).
+// p must be 32-byte aligned.
+__device__ __forceinline__ void store_2c128(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 }  // namespace fpa

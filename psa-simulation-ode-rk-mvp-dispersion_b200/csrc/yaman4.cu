@@ -144,8 +144,15 @@ __device__ __noinline__ void write_invalid_point(const Yaman4Params& p, int64_t 
 __device__ __forceinline__ void save_sample(const double (&y)[8], double*& tr, double (&pm)[4], bool trace,
                                             bool pmax) {
     if (trace) {
+        // one 64-byte row [A1..A4] per saved sample: two 256-bit stores = two full 32 B sectors
+        // (A_trace rows are 64-byte aligned whenever the buffer is 32-byte aligned; else 16 B stores)
+        if ((reinterpret_cast<uintptr_t>(tr) & 31) == 0) {
+            store_2c128(tr, y[0], y[1], y[2], y[3]);
+            store_2c128(tr + 4, y[4], y[5], y[6], y[7]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) store_c128(tr + 2 * j, y[2 * j], y[2 * j + 1]);
+            for (int j = 0; j < 4; ++j) store_c128(tr + 2 * j, y[2 * j], y[2 * j + 1]);
+        }
         tr += 8;
     }
     if (pmax) {

@@ -6,6 +6,7 @@ Public functions keep the reference's keyword signatures and return tuples:
     plot_max_signal_gain_vs_lambda_signal(...)     -> (x, gain_max)          scan_mismtach.py:262-430
     plot_max_gain_and_dbeta_vs_lambda_signal(...)  -> (x, gain_max, dbeta)   scan_mismtach.py:588-783
     scan_mismatch_seeded_signal(gain_mode)         -> 1-D dbeta sweep        scan_mismtach.py:43-259
+    plot_dbeta_vs_lambda_signal(...)               -> (x, dbeta)             scan_mismtach.py:473-585
 
 The reference runs `plan_from_wavelengths` + `compute_phase_mismatch` + `run_single_simulation`
 per point in a Python loop (:357-392, :694-738).  Here only the wavelength axes go to the GPU:
@@ -274,6 +275,55 @@ def plot_max_gain_and_dbeta_vs_lambda_signal(
 
     _figure(make, save_path, show)
     return x, gain_max, dbeta
+
+
+def plot_dbeta_vs_lambda_signal(
+        *, gamma: float, lambda_p1_m: float, lambda_p2_m: float, lambda_signal_m: Sequence[float],
+        p_in: Sequence[float], dispersion: DispersionParams, return_wavelength_unit: str = "nm",
+        xscale: str = "linear", yscale: str = "linear", length_unit: str = "m", show_progress: bool = True,
+        tqdm_desc: str = "Scanning dBeta(λ3)", title: Optional[str] = None, save_path: Optional[str] = None,
+        show: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """dBeta(lambda3) with the sign convention of the reference's private helper
+    (scan_mismtach.py:462-470): beta(w1)+beta(w2)-beta(w3)-beta(w4), Taylor to 4th order about the
+    dispersion's reference frequency -- i.e. MINUS the project-wide dbeta (dispersion.py:318).
+    NOTE: the reference's version returns all-NaN today (it looks for `disp.omega0`, which
+    DispersionParams does not have, and swallows the AttributeError, :433-438, :531-535); this is
+    what it computes once that lookup is pointed at `omega_ref`.  The table is built on the device
+    (`fpa_dbeta_table_host`); invalid points are NaN."""
+    lam3 = _signal_axis(lambda_signal_m)
+    p0 = np.asarray(list(p_in), dtype=float)
+    if p0.shape != (4,):
+        raise ValueError(f"p_in must have shape (4,), got {p0.shape}")
+    if not np.all(np.isfinite(p0)) or np.any(p0 < 0.0):
+        raise ValueError("p_in must contain finite non-negative powers")
+    xs = _norm_choice(xscale, ("linear", "log"), "xscale must be 'linear' or 'log'")
+    ys = _norm_choice(yscale, ("linear", "log"), "yscale must be 'linear' or 'log'")
+    plan, keep = _device.new_plan_desc([float(lambda_p1_m)], [float(lambda_p2_m)], lam3)
+    fill_plan_desc(plan, dispersion, PhaseMatchingConfig(method=PhaseMatchingMethod.GENERAL_TAYLOR, max_order=4))
+    dbeta = -_device.dbeta_table(plan)["dbeta"][0]
+    x, x_label = _x_axis(lam3, return_wavelength_unit)
+    ref = float(gamma) * float(p0[0] + p0[1])
+    if ys == "log" and (np.nanmin(dbeta) <= 0.0 or ref <= 0.0):
+        raise ValueError("yscale='log' requires dBeta and gamma*(P1+P2) to be strictly > 0.")
+    y_unit = "1/km" if str(length_unit).strip().lower() == "km" else "1/m"
+
+    def make(plt):
+        fig = plt.figure(figsize=(8.0, 5.0))
+        plt.plot(x, dbeta, label=r"$d\beta(\lambda_3)$")
+        plt.axhline(ref, linestyle="--", label=r"$\gamma(P_1+P_2)$")
+        plt.xlabel(x_label)
+        plt.ylabel(rf"$d\beta$ [{y_unit}]")
+        plt.xscale(xs)
+        plt.yscale(ys)
+        if title is not None:
+            plt.title(title)
+        plt.grid(True, which="both", linestyle="--", alpha=0.5)
+        plt.legend()
+        plt.tight_layout()
+        return fig
+
+    _figure(make, save_path, show)
+    return x, dbeta
 
 
 def sweep_dbeta_gain(*, cfg: SimulationConfig, delta_beta, gamma: float, alpha: float, p_in,

@@ -208,6 +208,19 @@ def test_golden_b4_main_sweep(gpu, golden):
     assert rel_err(g2, golden["b4_gain_lin_general"]) < TOL
 
 
+def test_dbeta_only_sweep(gpu, oracle, golden):
+    """plot_dbeta_vs_lambda_signal: the reference's helper convention (minus the project dbeta)."""
+    b2, b3, b4, wref = golden["b4_beta"]
+    lam3 = np.concatenate((golden["b4_lam"], [3e-7]))
+    x, d = gpu.scan_mismtach.plot_dbeta_vs_lambda_signal(
+        gamma=11.5e-3, lambda_p1_m=1550e-9, lambda_p2_m=1558e-9, lambda_signal_m=lam3, p_in=golden["b4_p_in"],
+        dispersion=_disp(gpu, b2, b3, b4, wref), show=False)
+    ref = [-oracle.phase_mismatch(oracle.plan_from_wavelengths(1550e-9, 1558e-9, l), oracle.Taylor(wref, 0, 0, b2, b3, b4),
+                                  oracle.GENERAL_TAYLOR) for l in golden["b4_lam"]]
+    assert np.array_equal(x[:-1], golden["b4_x"]) and np.isnan(d[-1])
+    assert rel_err(d[:-1], ref) < 1e-12
+
+
 def test_golden_config4_grid_nan_semantics(gpu, golden):
     b2, b3, b4, wref = golden["b4_beta"]
     cfg = gpu.config.custom_simulation_config(z_max=500.0, dz=0.2, save_every=10)

@@ -8,7 +8,7 @@ inputs and outputs, CUDA events).  Informational: bench.py carries the headline 
   config2    N = 21 dual-pump plan, single run, 10 000 steps, full trace
   config5    N = 64 comb, B in {1, 148}, 1 000 of the 1e5 steps (rate extrapolates linearly in z)
 
-usage: python tools/bench_extra.py > profiles/rN_extra.json
+usage: python tools/bench_extra.py [config1a config3 trace config2 config5] > profiles/rN_extra.json
 """
 import ctypes as C
 import json
@@ -31,6 +31,12 @@ torch.cuda.set_device(0)
 L.check(lib.fpa_set_device(0))
 stream = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
 out = {}
+ONLY = set(sys.argv[1:])
+
+
+def want(name):
+    return not ONLY or name in ONLY
+
 
 
 def timed(fn, reps=3, warm=1):
@@ -69,97 +75,103 @@ peak_tf, _ = fpa._device.fp64_peak(iters=2048)
 out["fp64_peak_tflops_measured"] = peak_tf
 
 # ---- config 1a: one run through the reference-shaped host API
-fp, ds = fpa.frequency_plan, fpa.dispersion
-om = fp.plan_from_wavelengths(1550e-9, 1560e-9, 1555e-9)
-sp = fp.infer_symmetry_from_omegas(*om)
-disp = ds.dispersion_params_from_D_S(fp.lambda_from_omega(sp.omega_c), 0.02, 0.02, 0.0, D_units="ps/nm/km",
-                                     S_units="ps/nm^2/km", dSdlmbd_units="ps/nm^3/km", omega_ref=sp.omega_c)
-cfg = fpa.config.custom_simulation_config(z_max=1000.0, dz=0.1, save_every=10)
-kw = dict(gamma=11.5e-3, alpha=float(np.log(10) / 10 * 0.9 / 1000), omega=om, p_in=[0.5, 0.5, 1e-5, 1e-5], dispersion=disp)
-fpa.simulation.run_single_simulation(cfg, **kw)
-t0 = time.perf_counter()
-for _ in range(5):
-    z, A = fpa.simulation.run_single_simulation(cfg, **kw)
-dt = (time.perf_counter() - t0) / 5
-out["config1a_single_run"] = {"steps": 10000, "saved": int(z.size), "wall_ms_per_call": 1e3 * dt,
-                              "point_steps_per_s": 10000 / dt, "note": "B = 1: one thread of one SM; latency-bound"}
+if want("config1a"):
+    fp, ds = fpa.frequency_plan, fpa.dispersion
+    om = fp.plan_from_wavelengths(1550e-9, 1560e-9, 1555e-9)
+    sp = fp.infer_symmetry_from_omegas(*om)
+    disp = ds.dispersion_params_from_D_S(fp.lambda_from_omega(sp.omega_c), 0.02, 0.02, 0.0, D_units="ps/nm/km",
+                                         S_units="ps/nm^2/km", dSdlmbd_units="ps/nm^3/km", omega_ref=sp.omega_c)
+    cfg = fpa.config.custom_simulation_config(z_max=1000.0, dz=0.1, save_every=10)
+    kw = dict(gamma=11.5e-3, alpha=float(np.log(10) / 10 * 0.9 / 1000), omega=om, p_in=[0.5, 0.5, 1e-5, 1e-5], dispersion=disp)
+    fpa.simulation.run_single_simulation(cfg, **kw)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        z, A = fpa.simulation.run_single_simulation(cfg, **kw)
+    dt = (time.perf_counter() - t0) / 5
+    out["config1a_single_run"] = {"steps": 10000, "saved": int(z.size), "wall_ms_per_call": 1e3 * dt,
+                                  "point_steps_per_s": 10000 / dt, "note": "B = 1: one thread of one SM; latency-bound"}
 
 # ---- config 3: 1e5-point dbeta sweep (reduce: A_end + Pmax), short and long
-B = 100_000
-dbeta = torch.linspace(-40.0, 40.0, B, dtype=torch.float64, device=dev) / 1000.0
-A0 = np.sqrt(np.array([0.1, 0.1, 1e-5, 0.0]))
-consts = torch.tensor([10.0 / 1000, 0.0] + [v for a in A0 for v in (a, 0.0)], dtype=torch.float64, device=dev)
-end = torch.empty(B * 8, dtype=torch.float64, device=dev)
-pmax = torch.empty(B * 4, dtype=torch.float64, device=dev)
-status = torch.empty(B, dtype=torch.int32, device=dev)
-for name, n_steps in (("config3_1e5x500", 500), ("config3_long_1e5x50000", 50000)):
-    d = yaman_desc(B, dbeta, consts, 500.0, n_steps, 10, L.OUT_END | L.OUT_PMAX | L.CHECK_NAN, end=end, pmax=pmax, status=status)
-    ms = timed(lambda: L.check(lib.fpa_yaman4_rk4_batch_dev(C.byref(d), stream())))
-    rate = B * n_steps / (ms * 1e-3)
-    out[name] = {"points": B, "steps": n_steps, "kernel_ms": ms, "point_steps_per_s": rate,
-                 "tflops": 568 * rate / 1e12, "frac_of_measured_fp64_peak": 568 * rate / 1e12 / peak_tf}
+if want("config3"):
+    B = 100_000
+    dbeta = torch.linspace(-40.0, 40.0, B, dtype=torch.float64, device=dev) / 1000.0
+    A0 = np.sqrt(np.array([0.1, 0.1, 1e-5, 0.0]))
+    consts = torch.tensor([10.0 / 1000, 0.0] + [v for a in A0 for v in (a, 0.0)], dtype=torch.float64, device=dev)
+    end = torch.empty(B * 8, dtype=torch.float64, device=dev)
+    pmax = torch.empty(B * 4, dtype=torch.float64, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    for name, n_steps in (("config3_1e5x500", 500), ("config3_long_1e5x50000", 50000)):
+        d = yaman_desc(B, dbeta, consts, 500.0, n_steps, 10, L.OUT_END | L.OUT_PMAX | L.CHECK_NAN, end=end, pmax=pmax, status=status)
+        ms = timed(lambda: L.check(lib.fpa_yaman4_rk4_batch_dev(C.byref(d), stream())))
+        rate = B * n_steps / (ms * 1e-3)
+        out[name] = {"points": B, "steps": n_steps, "kernel_ms": ms, "point_steps_per_s": rate,
+                     "tflops": 568 * rate / 1e12, "frac_of_measured_fp64_peak": 568 * rate / 1e12 / peak_tf}
 
 # ---- trace-mode write-out
-B = 200_000
-dbeta = torch.linspace(-0.015, 0.015, B, dtype=torch.float64, device=dev)
-A0 = np.sqrt(np.array([0.1, 0.1, 1e-7, 1e-7]))
-consts = torch.tensor([11.5e-3, 1.1512925464970228e-4] + [v for a in A0 for v in (a, 0.0)], dtype=torch.float64, device=dev)
-status = torch.empty(B, dtype=torch.int32, device=dev)
-for save_every in (10, 1):
-    n_steps = 2500
-    n_saved = n_steps // save_every + 1
-    trace = torch.empty(B * n_saved * 8, dtype=torch.float64, device=dev)
-    d = yaman_desc(B, dbeta, consts, 500.0, n_steps, save_every, L.OUT_TRACE | L.CHECK_NAN, trace=trace, status=status)
-    ms = timed(lambda: L.check(lib.fpa_yaman4_rk4_batch_dev(C.byref(d), stream())))
-    rate = B * n_steps / (ms * 1e-3)
-    out[f"trace_save_every_{save_every}"] = {
-        "points": B, "steps": n_steps, "n_saved": n_saved, "trace_bytes": B * n_saved * 64, "kernel_ms": ms,
-        "point_steps_per_s": rate, "frac_of_measured_fp64_peak": 568 * rate / 1e12 / peak_tf,
-        "hbm_write_GBps": B * n_saved * 64 / (ms * 1e-3) / 1e9}
-    del trace
-    torch.cuda.empty_cache()
+if want("trace"):
+    B = 200_000
+    dbeta = torch.linspace(-0.015, 0.015, B, dtype=torch.float64, device=dev)
+    A0 = np.sqrt(np.array([0.1, 0.1, 1e-7, 1e-7]))
+    consts = torch.tensor([11.5e-3, 1.1512925464970228e-4] + [v for a in A0 for v in (a, 0.0)], dtype=torch.float64, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    for save_every in (10, 1):
+        n_steps = 2500
+        n_saved = n_steps // save_every + 1
+        trace = torch.empty(B * n_saved * 8, dtype=torch.float64, device=dev)
+        d = yaman_desc(B, dbeta, consts, 500.0, n_steps, save_every, L.OUT_TRACE | L.CHECK_NAN, trace=trace, status=status)
+        ms = timed(lambda: L.check(lib.fpa_yaman4_rk4_batch_dev(C.byref(d), stream())))
+        rate = B * n_steps / (ms * 1e-3)
+        out[f"trace_save_every_{save_every}"] = {
+            "points": B, "steps": n_steps, "n_saved": n_saved, "trace_bytes": B * n_saved * 64, "kernel_ms": ms,
+            "point_steps_per_s": rate, "frac_of_measured_fp64_peak": 568 * rate / 1e12 / peak_tf,
+            "hbm_write_GBps": B * n_saved * 64 / (ms * 1e-3) / 1e9}
+        del trace
+        torch.cuda.empty_cache()
 
 # ---- config 2: N = 21
-nw = fpa.nwave
-plan = nw.uniform_comb_plan(sp.omega_c, sp.omega_d / 5.0, range(-10, 11))
-beta = nw.beta_per_wave(plan, disp)
-p_in = np.zeros(21)
-p_in[[5, 15]] = 0.5
-p_in[[9, 11]] = 1e-5
-for form in ("table", "comb"):
-    r = nw.run_nwave_simulation(cfg, plan, gamma=11.5e-3, alpha=kw["alpha"], p_in=p_in, beta=beta, form=form)
-    t0 = time.perf_counter()
-    r = nw.run_nwave_simulation(cfg, plan, gamma=11.5e-3, alpha=kw["alpha"], p_in=p_in, beta=beta, form=form)
-    dt = time.perf_counter() - t0
-    out[f"config2_n21_single_run_{form}"] = {
-        "waves": 21, "triplets": plan.n_triplets, "steps": 10000, "wall_ms": 1e3 * dt,
-        "point_steps_per_s": 10000 / dt, "gflops_credited": plan.flops_per_step(form) * 10000 / dt / 1e9,
-        "trace_shape": list(r["A_trace"].shape)}
+if want("config2"):
+    nw = fpa.nwave
+    plan = nw.uniform_comb_plan(sp.omega_c, sp.omega_d / 5.0, range(-10, 11))
+    beta = nw.beta_per_wave(plan, disp)
+    p_in = np.zeros(21)
+    p_in[[5, 15]] = 0.5
+    p_in[[9, 11]] = 1e-5
+    for form in ("table", "comb"):
+        r = nw.run_nwave_simulation(cfg, plan, gamma=11.5e-3, alpha=kw["alpha"], p_in=p_in, beta=beta, form=form)
+        t0 = time.perf_counter()
+        r = nw.run_nwave_simulation(cfg, plan, gamma=11.5e-3, alpha=kw["alpha"], p_in=p_in, beta=beta, form=form)
+        dt = time.perf_counter() - t0
+        out[f"config2_n21_single_run_{form}"] = {
+            "waves": 21, "triplets": plan.n_triplets, "steps": 10000, "wall_ms": 1e3 * dt,
+            "point_steps_per_s": 10000 / dt, "gflops_credited": plan.flops_per_step(form) * 10000 / dt / 1e9,
+            "trace_shape": list(r["A_trace"].shape)}
 
 # ---- config 5: N = 64 comb
-w0 = 2 * np.pi * 299792458.0 / 1550e-9
-plan64 = nw.uniform_comb_plan(w0, 2 * np.pi * 100e9, range(-32, 32))
-disp64 = ds.DispersionParams(omega_ref=w0, beta2=-2.57e-29, beta3=3.30e-41, beta4=-1.63e-55)
-beta64 = nw.beta_per_wave(plan64, disp64)
-rng = np.random.default_rng(0)
-phases = rng.uniform(0, 2 * np.pi, 64)
-cfg5 = fpa.config.custom_simulation_config(z_max=100.0, dz=0.1, save_every=100)   # 1 000 of the 1e5 steps
-for Bn, form in ((1, "table"), (148, "table"), (1, "comb"), (148, "comb"), (1024, "comb")):
-    A0n = np.empty((Bn, 64), dtype=complex)
-    for b, pw in enumerate(np.linspace(0.1, 1.0, Bn)):
-        p = np.full(64, 1e-12)
-        p[33] = 1e-6
-        p[[28, 36]] = pw
-        A0n[b] = np.sqrt(p) * np.exp(1j * phases)
-    run = lambda: nw.run_nwave_simulation(cfg5, plan64, gamma=11.5e-3, alpha=2e-4, A0=A0n, beta=beta64,  # noqa: E731
-                                          outputs=("end",), form=form)
-    run()
-    t0 = time.perf_counter()
-    run()
-    dt = time.perf_counter() - t0
-    out[f"config5_n64_B{Bn}_{form}"] = {
-        "waves": 64, "triplets": plan64.n_triplets, "steps_timed": 1000, "wall_ms": 1e3 * dt,
-        "point_steps_per_s": Bn * 1000 / dt,
-        "tflops_credited": plan64.flops_per_step(form) * Bn * 1000 / dt / 1e12,
-        "full_1e5_steps_estimate_s": dt * 100}
+if want("config5"):
+    w0 = 2 * np.pi * 299792458.0 / 1550e-9
+    plan64 = nw.uniform_comb_plan(w0, 2 * np.pi * 100e9, range(-32, 32))
+    disp64 = ds.DispersionParams(omega_ref=w0, beta2=-2.57e-29, beta3=3.30e-41, beta4=-1.63e-55)
+    beta64 = nw.beta_per_wave(plan64, disp64)
+    rng = np.random.default_rng(0)
+    phases = rng.uniform(0, 2 * np.pi, 64)
+    cfg5 = fpa.config.custom_simulation_config(z_max=100.0, dz=0.1, save_every=100)   # 1 000 of the 1e5 steps
+    for Bn, form in ((1, "table"), (148, "table"), (1, "comb"), (148, "comb"), (1024, "comb")):
+        A0n = np.empty((Bn, 64), dtype=complex)
+        for b, pw in enumerate(np.linspace(0.1, 1.0, Bn)):
+            p = np.full(64, 1e-12)
+            p[33] = 1e-6
+            p[[28, 36]] = pw
+            A0n[b] = np.sqrt(p) * np.exp(1j * phases)
+        run = lambda: nw.run_nwave_simulation(cfg5, plan64, gamma=11.5e-3, alpha=2e-4, A0=A0n, beta=beta64,  # noqa: E731
+                                              outputs=("end",), form=form)
+        run()
+        t0 = time.perf_counter()
+        run()
+        dt = time.perf_counter() - t0
+        out[f"config5_n64_B{Bn}_{form}"] = {
+            "waves": 64, "triplets": plan64.n_triplets, "steps_timed": 1000, "wall_ms": 1e3 * dt,
+            "point_steps_per_s": Bn * 1000 / dt,
+            "tflops_credited": plan64.flops_per_step(form) * Bn * 1000 / dt / 1e12,
+            "full_1e5_steps_estimate_s": dt * 100}
+
 print(json.dumps(out, indent=1))
