@@ -54,10 +54,16 @@ FLOPS_PER_POINT_STEP = 568.0
 NCU_DRAM_BYTES_PER_LAUNCH = 111872.0
 
 
-def workload_axes(rank: int, world: int):
-    """Rank's slice of the (1000*world) x 1000 wavelength grid (weak scaling)."""
-    lam1_all = np.linspace(1545e-9, 1555e-9, N1 * world)
+def workload_axes(rank: int, world: int, scaling: str = "weak"):
+    """Rank's slice of the wavelength grid: weak scaling = 1000 pump rows per rank of a (1000*world) x 1000
+    grid; strong scaling = the rank's contiguous share of the fixed 1000 x 1000 grid."""
     lam3 = np.linspace(1540e-9, 1565e-9, N3)
+    if scaling == "strong":
+        lam1_all = np.linspace(1545e-9, 1555e-9, N1)
+        base, extra = divmod(N1, world)
+        lo = rank * base + min(rank, extra)
+        return lam1_all[lo:lo + base + (1 if rank < extra else 0)].copy(), lam3
+    lam1_all = np.linspace(1545e-9, 1555e-9, N1 * world)
     return lam1_all[rank * N1:(rank + 1) * N1].copy(), lam3
 
 
@@ -207,14 +213,16 @@ def run_ours(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    lam1, lam3 = workload_axes(rank, world)
+    lam1, lam3 = workload_axes(rank, world, args.scaling)
+    n1 = lam1.size                      # pump rows of this rank
     odisp = fiber_dispersion(O)
     disp = fpa.dispersion.DispersionParams(omega_ref=odisp.omega_ref, beta2=odisp.b[2], beta3=odisp.b[3],
                                            beta4=odisp.b[4])
     pm_cfg = fpa.phase_matching.PhaseMatchingConfig()        # SYMMETRIC_EVEN (2,4): the reference default
     cfg = fpa.config.custom_simulation_config(z_max=Z_MAX, dz=DZ, save_every=SAVE_EVERY)
     n_steps = int(round(Z_MAX / DZ))
-    B = N1 * N3
+    B = n1 * N3
+    total_points = world * B if args.scaling == "weak" else N1 * N3
 
     # ---- device-resident sweep descriptor (inputs already in HBM)
     t_l1 = torch.from_numpy(lam1).to(dev)
@@ -227,10 +235,10 @@ def run_ours(args) -> None:
     scratch_bytes = int(lib.fpa_yaman4_sweep_scratch_bytes(B))        # 0: the sweep is one fused kernel
     t_scratch = torch.empty(max(scratch_bytes, 16), dtype=torch.uint8, device=dev)
     t_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    t_all = torch.empty(world * B, dtype=torch.float64, device=dev) if world > 1 else None
+    t_all = torch.empty(world * B, dtype=torch.float64, device=dev) if (world > 1 and args.scaling == "weak") else None
 
     d = L.SweepDesc()
-    d.plan.n1, d.plan.n3 = N1, N3
+    d.plan.n1, d.plan.n3 = n1, N3
     d.plan.lambda1, d.plan.lambda2, d.plan.lambda3 = t_l1.data_ptr(), t_l2.data_ptr(), t_l3.data_ptr()
     d.plan.lambda2_stride = 0
     fpa.phase_matching.fill_plan_desc(d.plan, disp, pm_cfg)
@@ -248,8 +256,10 @@ def run_ours(args) -> None:
         t_flush.zero_()                                                    # L2 flush between steps
         stream = torch.cuda.current_stream().cuda_stream
         L.check(lib.fpa_yaman4_sweep_dev(C.byref(d), t_scratch.data_ptr(), scratch_bytes, stream))
-        if world > 1:
+        if world > 1 and t_all is not None:
             dist.all_gather_into_tensor(t_all, t_gain)                     # the final result gather
+        elif world > 1:                                                    # strong scaling: ragged row blocks
+            fpa.sharding.gather_rows(t_gain.view(n1, N3), N1, dist, world, rank)
 
     def barrier():
         if world > 1:
@@ -277,7 +287,7 @@ def run_ours(args) -> None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    value = world * B * n_steps * args.steps / (ms_total * 1e-3)
+    value = total_points * n_steps * args.steps / (ms_total * 1e-3)
 
     # ---- the RK4 integrator alone (no plan prologue / gain epilogue), for the roofline
     yd = L.Yaman4Desc()
@@ -313,10 +323,10 @@ def run_ours(args) -> None:
         buf = (C.c_char * n).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype).reshape(shape), p
 
-    h_l1, p1 = pinned((N1,), np.float64)
+    h_l1, p1 = pinned((n1,), np.float64)
     h_l3, p3 = pinned((N3,), np.float64)
     h_l1[:], h_l3[:] = lam1, lam3
-    out_bufs = {k: pinned((N1, N3), dt) for k, dt in
+    out_bufs = {k: pinned((n1, N3), dt) for k, dt in
                 (("gain_lin", np.float64), ("dbeta", np.float64), ("valid", np.int32), ("status", np.int32))}
     out_arrays = {k: v[0] for k, v in out_bufs.items()}
 
@@ -338,10 +348,10 @@ def run_ours(args) -> None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * B * n_steps * e2e_steps / e2e_s
-    h2d = (N1 + 1 + N3) * 8
+    e2e_value = total_points * n_steps * e2e_steps / e2e_s
+    h2d = (n1 + 1 + N3) * 8
     d2h = B * (8 + 8 + 4 + 4)
-    gain_dev = t_gain.cpu().numpy().reshape(N1, N3)
+    gain_dev = t_gain.cpu().numpy().reshape(n1, N3)
     assert np.array_equal(res["gain_lin"], gain_dev, equal_nan=True), "e2e and device-resident sweeps differ"
 
     if rank != 0:
@@ -358,7 +368,7 @@ def run_ours(args) -> None:
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "sweep2d_1000x1000_x2500steps (BASELINE configs[3]: pump x signal wavelength "
                                "sweep, 1e6 scan points per GPU, z_max=500 m, dz=0.2 m, save_every=10, "
                                "SYMMETRIC_EVEN(2,4) dbeta, max-over-saved signal gain)",
@@ -381,7 +391,7 @@ def run_ours(args) -> None:
                      "hbm_note": "reduce-mode sweep: ~56 B per point per launch, HBM is idle"},
         "device": name.value.decode(),
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.scaling == "weak":
         cores = os.cpu_count() or 1
         n_pts = max(16, 2 * cores)
         cpu_value, wall, idx, cpu_gain = cpu_sample(n_pts, cores, seed=0)
@@ -403,6 +413,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): 1e6 points per GPU; strong: the fixed 1e6-point grid split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true",
                     help="skip the CPU oracle leg (profiling runs under ncu)")
     args = ap.parse_args()
