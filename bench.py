@@ -49,9 +49,9 @@ P_IN = [0.1, 0.1, 1e-7, 1e-7]
 LAM_P2 = 1558e-9
 FLOPS_PER_POINT_STEP = 568.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused sweep kernel on this workload,
-# from the committed ncu capture (cannot be measured outside a profiler): 109.8 KB read + 2.0 KB written --
+# from the committed ncu capture (cannot be measured outside a profiler): 81.9 KB read + 0 B written --
 # the 24 MB of per-point results are still in the 126 MB L2 when the kernel ends
-NCU_DRAM_BYTES_PER_LAUNCH = 111872.0
+NCU_DRAM_BYTES_PER_LAUNCH = 81920.0
 
 
 def workload_axes(rank: int, world: int, scaling: str = "weak"):

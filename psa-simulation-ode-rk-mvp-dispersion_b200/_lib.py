@@ -23,8 +23,6 @@ PM_GENERAL_TAYLOR, PM_SYMMETRIC_EVEN, PM_PROVIDED = 0, 1, 2
 MAX_TAYLOR_ORDER = 12
 
 c_dp = C.POINTER(C.c_double)
-c_ip = C.POINTER(C.c_int32)
-c_lp = C.POINTER(C.c_int64)
 
 
 class Yaman4Desc(C.Structure):

@@ -15,7 +15,7 @@ import numpy as np
 
 from ._checks import four, nonneg, positive, real
 from .dispersion import DispersionParams
-from .frequency_plan import SymmetricPlan, plan_from_omegas, plan_from_symmetry, plan_from_wavelengths
+from .frequency_plan import SymmetricPlan, plan_from_omegas, plan_from_wavelengths
 from .phase_matching import PhaseMatchingConfig, PhaseMatchingMethod
 
 WAVE_ORDER: Tuple[str, str, str, str] = ("pump1", "pump2", "signal", "idler")

@@ -19,8 +19,6 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 SRC = ROOT / "psa-simulation-ode-rk-mvp-dispersion_b200" / "csrc" / "yaman4.cu"
 WORK = Path("/tmp/search")
-sys.path.insert(0, str(ROOT / "tools"))
-import sass_cost as sc  # noqa: E402
 
 # the four terms of every component: (multiplicand a, multiplicand b) with sign folded into a
 TERMS = [
