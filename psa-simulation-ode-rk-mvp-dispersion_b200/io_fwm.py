@@ -146,3 +146,39 @@ def save_sweep_npz(path, *, axes: dict, results: dict, metadata=None, overwrite:
     p.parent.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(p, metadata_json=np.array(md_json), **arrays)
     return p
+
+
+def save_sweep_csv(path, *, columns: dict, overwrite: bool = False) -> Path:
+    """One row per scan point: `columns` maps header -> 1-D array (all of one length), e.g.
+    {"lambda3_nm": x, "gain_dB": g, "dbeta_1_m": d}.  NaN entries are written as 'nan'."""
+    p = _target(path, ".csv", overwrite)
+    cols = {k: np.asarray(v).reshape(-1) for k, v in columns.items()}
+    sizes = {v.size for v in cols.values()}
+    if len(sizes) != 1:
+        raise ValueError("all columns must have the same length")
+    p.parent.mkdir(parents=True, exist_ok=True)
+    with p.open("w", encoding="utf-8", newline="") as fh:
+        writer = csv.writer(fh)
+        writer.writerow(list(cols))
+        for row in zip(*cols.values()):
+            writer.writerow([v.item() if hasattr(v, "item") else v for v in row])
+    return p
+
+
+def save_sweep_bundle(output_dir, run_name: str, *, axes: dict, results: dict, metadata=None,
+                      overwrite: bool = False) -> dict:
+    """Sweep analogue of save_run_bundle: <run_name>.npz (axes + result maps + metadata_json),
+    <run_name>.json (metadata) and, for 1-D sweeps, <run_name>.csv (one row per scan point)."""
+    out_dir = _ensure_path(output_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    md = _make_metadata(metadata)
+    saved = {
+        "npz": save_sweep_npz(out_dir / f"{run_name}.npz", axes=axes, results=results, metadata=md,
+                              overwrite=overwrite),
+        "json": save_metadata_json(out_dir / f"{run_name}.json", md, overwrite=overwrite),
+    }
+    flat = {k: np.asarray(v) for k, v in {**axes, **results}.items() if isinstance(v, np.ndarray)}
+    one_d = {k: v for k, v in flat.items() if v.ndim == 1}
+    if one_d and len({v.size for v in one_d.values()}) == 1 and len(one_d) == len(flat):
+        saved["csv"] = save_sweep_csv(out_dir / f"{run_name}.csv", columns=one_d, overwrite=overwrite)
+    return saved

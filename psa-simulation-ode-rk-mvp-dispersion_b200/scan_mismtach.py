@@ -326,6 +326,33 @@ def plot_dbeta_vs_lambda_signal(
     return x, dbeta
 
 
+def sweep_peak(x, gain) -> dict:
+    """Location of the best scan point (the reference prints it after its dbeta scan,
+    scan_mismtach.py:183-199): index (unravelled for 2-D maps), abscissa and gain; NaNs ignored."""
+    g = np.asarray(gain, dtype=float)
+    if g.size == 0 or np.all(np.isnan(g)):
+        raise ValueError("no finite gain in the sweep")
+    flat = int(np.nanargmax(g))
+    idx = np.unravel_index(flat, g.shape)
+    xs = np.asarray(x)
+    return {"index": idx if g.ndim > 1 else idx[0], "gain": float(g[idx]),
+            "x": xs[idx[-1]].item() if xs.ndim == 1 else xs[idx].item()}
+
+
+def rerun_point_with_trace(*, cfg: SimulationConfig, lambda_p1_m: float, lambda_p2_m: float,
+                           lambda_signal_m: float, gamma: float, alpha: float, p_in, phase_in=None,
+                           dispersion: Optional[DispersionParams] = None,
+                           phase_matching_cfg: Optional[PhaseMatchingConfig] = None, length_unit: str = "m"):
+    """Full (z, A[n_saved, 4]) trace of ONE scan point of a wavelength sweep -- what a user runs on the
+    best point of a reduce-mode sweep to look at the evolution (the (z, A) layout plotting.py consumes)."""
+    from .frequency_plan import plan_from_wavelengths
+    from .simulation import run_single_simulation
+    omega = plan_from_wavelengths(float(lambda_p1_m), float(lambda_p2_m), float(lambda_signal_m))
+    return run_single_simulation(cfg, gamma=gamma, alpha=alpha, omega=omega, p_in=p_in, phase_in=phase_in,
+                                 dispersion=dispersion, phase_matching_cfg=phase_matching_cfg,
+                                 length_unit=length_unit)
+
+
 def sweep_dbeta_gain(*, cfg: SimulationConfig, delta_beta, gamma: float, alpha: float, p_in,
                      phase_in=None, length_unit: str = "km", gain_mode: GainMode = "end",
                      device: Optional[int] = None) -> dict:

@@ -208,6 +208,21 @@ def test_golden_b4_main_sweep(gpu, golden):
     assert rel_err(g2, golden["b4_gain_lin_general"]) < TOL
 
 
+def test_best_point_rerun_with_trace(gpu, golden):
+    """Reduce-mode sweep -> peak -> full trace of the best point: the trace's max equals the sweep's gain."""
+    b2, b3, b4, wref = golden["b4_beta"]
+    cfg = gpu.config.custom_simulation_config(z_max=500.0, dz=0.2, save_every=10)
+    kw = dict(cfg=cfg, lambda_p1_m=1550e-9, lambda_p2_m=1558e-9, gamma=11.5e-3, alpha=float(golden["b4_alpha"][0]),
+              p_in=golden["b4_p_in"], dispersion=_disp(gpu, b2, b3, b4, wref))
+    x, g, d = gpu.scan_mismtach.plot_max_gain_and_dbeta_vs_lambda_signal(
+        lambda_signal_m=golden["b4_lam"], gain_unit="linear", show=False, **kw)
+    pk = gpu.scan_mismtach.sweep_peak(x, g)
+    assert pk["index"] == int(np.nanargmax(golden["b4_gain_db"]))
+    z, A = gpu.scan_mismtach.rerun_point_with_trace(lambda_signal_m=golden["b4_lam"][pk["index"]], **kw)
+    assert A.shape == (251, 4) and z[-1] == 500.0
+    assert rel_err((np.abs(A[:, 2]) ** 2).max() / golden["b4_p_in"][2], pk["gain"]) < 1e-12
+
+
 def test_dbeta_only_sweep(gpu, oracle, golden):
     """plot_dbeta_vs_lambda_signal: the reference's helper convention (minus the project dbeta)."""
     b2, b3, b4, wref = golden["b4_beta"]

@@ -206,3 +206,63 @@ def test_io_fwm_round_trip(fpa, golden, tmp_path):
                            metadata={"n": 3})
     with np.load(sp) as raw:
         assert set(raw.files) == {"metadata_json", "axis_lam3", "gain"}
+
+
+def test_sweep_outputs_and_peak(fpa, tmp_path):
+    io, S = fpa.io_fwm, fpa.scan_mismtach
+    x = np.linspace(1540.0, 1565.0, 6)
+    gain = np.array([0.1, np.nan, 7.5, 7.7, 2.0, 0.0])
+    dbeta = np.linspace(-0.01, 0.01, 6)
+    assert S.sweep_peak(x, gain) == {"index": 3, "gain": 7.7, "x": 1555.0}
+    pk = S.sweep_peak(x, np.vstack([gain, gain + 1.0]))
+    assert pk["index"] == (1, 3) and pk["gain"] == 8.7 and pk["x"] == 1555.0
+    with pytest.raises(ValueError):
+        S.sweep_peak(x, np.full(6, np.nan))
+    saved = io.save_sweep_bundle(tmp_path / "sw", "scan", axes={"lambda3_nm": x},
+                                 results={"gain_dB": gain, "dbeta_1_m": dbeta}, metadata={"gamma": 0.0115})
+    assert set(saved) == {"npz", "json", "csv"}
+    rows = saved["csv"].read_text().strip().splitlines()
+    assert rows[0] == "lambda3_nm,gain_dB,dbeta_1_m" and len(rows) == 7 and rows[2].split(",")[1] == "nan"
+    with np.load(saved["npz"]) as raw:
+        assert np.array_equal(raw["gain_dB"], gain, equal_nan=True) and "axis_lambda3_nm" in raw.files
+    two_d = io.save_sweep_bundle(tmp_path / "sw", "map", axes={"lam1": x[:2], "lam3": x},
+                                 results={"gain": np.zeros((2, 6))})
+    assert set(two_d) == {"npz", "json"}                       # no per-point CSV for a 2-D map
+    with pytest.raises(ValueError):
+        io.save_sweep_csv(tmp_path / "bad", columns={"a": np.zeros(2), "b": np.zeros(3)})
+
+
+def test_reference_main_script_imports_against_the_drop_in(fpa):
+    """alias the reference's module names to this package and import the
+    reference's own main.py unchanged (build container only: needs /root/reference; matplotlib is
+    stubbed).  Every name main.py imports must resolve here."""
+    import importlib.util
+    import sys
+    import types
+    from pathlib import Path
+    ref_main = Path("/root/reference/main.py")
+    if not ref_main.exists():
+        pytest.skip("reference checkout not present on this machine")
+    names = ("config", "constants", "frequency_plan", "dispersion", "phase_matching", "parameters", "integrators",
+             "yaman_model", "simulation", "scan_mismtach", "io_fwm")
+    saved = {n: sys.modules.get(n) for n in names + ("plotting", "main")}
+    try:
+        for n in names:
+            sys.modules[n] = getattr(fpa, n)
+        plotting = types.ModuleType("plotting")          # presentation layer: out of scope, stubbed
+        plotting.__getattr__ = lambda attr: (lambda *a, **k: None)
+        sys.modules["plotting"] = plotting
+        spec = importlib.util.spec_from_file_location("main", ref_main)
+        mod = importlib.util.module_from_spec(spec)
+        sys.dont_write_bytecode = True
+        spec.loader.exec_module(mod)                       # runs main.py's imports and defs (not __main__)
+        for fn in ("main_single_simulation", "main_gain_spectrum", "main_gain_spectrum_dbeta"):
+            assert callable(getattr(mod, fn))
+        assert mod.run_single_simulation is fpa.simulation.run_single_simulation
+        assert mod.plot_max_gain_and_dbeta_vs_lambda_signal is fpa.scan_mismtach.plot_max_gain_and_dbeta_vs_lambda_signal
+    finally:
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
