@@ -58,6 +58,7 @@ struct Yaman4Params {
     int           gamma_stride, alpha_stride, A0_stride;
     int           n_steps, save_every;
     int           check;
+    int           lossless;  // uniform physics with alpha == 0
     int64_t       n_saved;
     Yaman4Coef    coef;  // valid when gamma and alpha are the same for every point (UNIFORM)
 };
@@ -79,6 +80,7 @@ __host__ __device__ inline Yaman4Coef make_coef(double gamma, double alpha, doub
 // One RK4 stage.  in = stage state (x1,y1,..,x4,y4), base = what the weighted RHS is added to,
 // (qr,qi) = c*2*gamma*exp(i*dbeta*z) for this stage's weight c, cg/c2g/cn the matching
 // coefficients.  out = base + c*f(in): 32 shared + 32 chain FP64 instructions.  S = sum |in|^2.
+template <bool LOSS = true>
 __device__ __forceinline__ void stage(const double (&in)[8], const double (&base)[8], double qr, double qi,
                                       double cg, double c2g, double cn, double (&out)[8], double& S) {
     const double x1 = in[0], y1 = in[1], x2 = in[2], y2 = in[3];
@@ -103,14 +105,25 @@ __device__ __forceinline__ void stage(const double (&in)[8], const double (&base
     const double Zr = fma(qi, Vi, qr * Vr),  Zi = fma(qr, Vi, -(qi * Vr));
     // out_j = base_j + cn*A_j + i*G_j*A_j + i*conj(A_m)*{W|Z}
     //   i*conj(A_m)*W = (ym Wr - xm Wi) + i (xm Wr + ym Wi)
-    out[0] = fma(cn, x1, fma(-G1, y1, fma(y2, Wr, fma(-x2, Wi, base[0]))));
-    out[1] = fma(cn, y1, fma(G1, x1, fma(x2, Wr, fma(y2, Wi, base[1]))));
-    out[2] = fma(cn, x2, fma(-G2, y2, fma(y1, Wr, fma(-x1, Wi, base[2]))));
-    out[3] = fma(cn, y2, fma(G2, x2, fma(x1, Wr, fma(y1, Wi, base[3]))));
-    out[4] = fma(cn, x3, fma(-G3, y3, fma(y4, Zr, fma(-x4, Zi, base[4]))));
-    out[5] = fma(cn, y3, fma(G3, x3, fma(x4, Zr, fma(y4, Zi, base[5]))));
-    out[6] = fma(cn, x4, fma(-G4, y4, fma(y3, Zr, fma(-x3, Zi, base[6]))));
-    out[7] = fma(cn, y4, fma(G4, x4, fma(x3, Zr, fma(y3, Zi, base[7]))));
+    if (LOSS) {
+        out[0] = fma(cn, x1, fma(-G1, y1, fma(y2, Wr, fma(-x2, Wi, base[0]))));
+        out[1] = fma(cn, y1, fma(G1, x1, fma(x2, Wr, fma(y2, Wi, base[1]))));
+        out[2] = fma(cn, x2, fma(-G2, y2, fma(y1, Wr, fma(-x1, Wi, base[2]))));
+        out[3] = fma(cn, y2, fma(G2, x2, fma(x1, Wr, fma(y1, Wi, base[3]))));
+        out[4] = fma(cn, x3, fma(-G3, y3, fma(y4, Zr, fma(-x4, Zi, base[4]))));
+        out[5] = fma(cn, y3, fma(G3, x3, fma(x4, Zr, fma(y4, Zi, base[5]))));
+        out[6] = fma(cn, x4, fma(-G4, y4, fma(y3, Zr, fma(-x3, Zi, base[6]))));
+        out[7] = fma(cn, y4, fma(G4, x4, fma(x3, Zr, fma(y3, Zi, base[7]))));
+    } else {  // alpha == 0: the reference's loss term is exact zeros (yaman_model.py:129-130)
+        out[0] = fma(-G1, y1, fma(y2, Wr, fma(-x2, Wi, base[0])));
+        out[1] = fma(G1, x1, fma(x2, Wr, fma(y2, Wi, base[1])));
+        out[2] = fma(-G2, y2, fma(y1, Wr, fma(-x1, Wi, base[2])));
+        out[3] = fma(G2, x2, fma(x1, Wr, fma(y1, Wi, base[3])));
+        out[4] = fma(-G3, y3, fma(y4, Zr, fma(-x4, Zi, base[4])));
+        out[5] = fma(G3, x3, fma(x4, Zr, fma(y4, Zi, base[5])));
+        out[6] = fma(-G4, y4, fma(y3, Zr, fma(-x3, Zi, base[6])));
+        out[7] = fma(G4, x4, fma(x3, Zr, fma(y3, Zi, base[7])));
+    }
 }
 
 __device__ __forceinline__ void load_state(const Yaman4Params& p, int64_t b, double (&y)[8]) {
@@ -187,7 +200,7 @@ __device__ __forceinline__ void write_results(const Yaman4Params& p, int64_t b, 
 
 // The z-loop of the fast path: advances y over all steps, keeps the running maxima in pm and
 // returns the first step whose result was not finite (or FPA_POINT_OK).
-template <bool TRACE, bool PMAX>
+template <bool TRACE, bool PMAX, bool LOSS>
 __device__ __forceinline__ int32_t fast_integrate(const Yaman4Params& p, int64_t b, double dbeta,
                                                   const Yaman4Coef& cf, double (&y)[8], double (&pm)[4]) {
     double* tr = nullptr;
@@ -230,7 +243,7 @@ __device__ __forceinline__ int32_t fast_integrate(const Yaman4Params& p, int64_t
 
         double ys[8], yt[8], acc[8], S, Sx;
         // stage 1: ys = y + (h/2) f(z, y)
-        stage(y, y, qr, qi, cf.cg[0], cf.c2g[0], cf.cn[0], ys, S);
+        stage<LOSS>(y, y, qr, qi, cf.cg[0], cf.c2g[0], cf.cn[0], ys, S);
         // S = sum |A|^2 of the state that step i-1 produced: a non-finite component makes S
         // non-finite, so the exact per-component test runs only then (integrators.py:132-135).
         if (nonfinite(S) && bad == FPA_POINT_OK && i > 0) {
@@ -242,15 +255,15 @@ __device__ __forceinline__ int32_t fast_integrate(const Yaman4Params& p, int64_t
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fma(third, ys[j], y[j] * (-third));
         // stage 2: yt = y + (h/2) f(z+h/2, ys)
-        stage(ys, y, qhr, qhi, cf.cg[0], cf.c2g[0], cf.cn[0], yt, Sx);
+        stage<LOSS>(ys, y, qhr, qhi, cf.cg[0], cf.c2g[0], cf.cn[0], yt, Sx);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fma(two_thirds, yt[j], acc[j]);
         // stage 3: ys = y + h f(z+h/2, yt)
-        stage(yt, y, q2r, q2i, cf.cg[1], cf.c2g[1], cf.cn[1], ys, Sx);
+        stage<LOSS>(yt, y, q2r, q2i, cf.cg[1], cf.c2g[1], cf.cn[1], ys, Sx);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fma(third_c, ys[j], acc[j]);
         // stage 4: y' = acc + (h/6) f(z+h, ys)
-        stage(ys, acc, q6r, q6i, cf.cg[2], cf.c2g[2], cf.cn[2], y, Sx);
+        stage<LOSS>(ys, acc, q6r, q6i, cf.cg[2], cf.c2g[2], cf.cn[2], y, Sx);
 
         qr = qfr;
         qi = qfi;
@@ -263,7 +276,9 @@ __device__ __forceinline__ int32_t fast_integrate(const Yaman4Params& p, int64_t
     return bad;
 }
 
-template <bool TRACE, bool PMAX, bool UNIFORM, int THREADS, int MIN_BLOCKS>
+// UNIFORM: 0 = gamma/alpha per thread; 1 = uniform physics, coefficients from the constant bank;
+// 2 = uniform and lossless (alpha == 0): the 32 loss FMAs per step are not issued.
+template <bool TRACE, bool PMAX, int UNIFORM, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_fast_kernel(const Yaman4Params p) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.n_points) return;
@@ -278,13 +293,13 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_fast_kernel(const 
     // stage-weighted coefficients: from the constant bank when the physics is uniform over the
     // batch (sweeps), else per thread
     Yaman4Coef cf;
-    if (UNIFORM) {
+    if (UNIFORM != 0) {
         cf = p.coef;
     } else {
         cf = make_coef(p.gamma[b * p.gamma_stride], p.alpha[b * p.alpha_stride], p.h);
     }
     double        pm[4] = {0.0, 0.0, 0.0, 0.0};
-    const int32_t bad = fast_integrate<TRACE, PMAX>(p, b, dbeta, cf, y, pm);
+    const int32_t bad = fast_integrate<TRACE, PMAX, UNIFORM != 2>(p, b, dbeta, cf, y, pm);
     write_results(p, b, y, pm, PMAX, bad);
 }
 
@@ -305,7 +320,7 @@ struct SweepExtra {
     double*    gain_lin;    // [B]
 };
 
-template <int THREADS, int MIN_BLOCKS>
+template <bool LOSS, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_sweep_kernel(const Yaman4Params p, const SweepExtra x) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.n_points) return;
@@ -342,7 +357,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_sweep_kernel(const
         if (p.status) p.status[b] = p.check ? 0 : FPA_POINT_OK;
     } else {
         double  pm[4] = {0.0, 0.0, 0.0, 0.0};
-        int32_t bad = fast_integrate<false, true>(p, b, db_run, p.coef, y, pm);
+        int32_t bad = fast_integrate<false, true, LOSS>(p, b, db_run, p.coef, y, pm);
         if (p.check && bad == FPA_POINT_OK) {
             bool nf = false;
 #pragma unroll
@@ -373,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_sweep_kernel(const
 __device__ __forceinline__ void rhs4(const double (&y)[8], double pr, double pi, double gamma,
                                      double nha, double (&k)[8], double& Ssum) {
     const double zero[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    stage(y, zero, pr, pi, gamma, gamma + gamma, nha, k, Ssum);
+    stage<true>(y, zero, pr, pi, gamma, gamma + gamma, nha, k, Ssum);
 }
 
 template <bool GRID>
@@ -494,10 +509,12 @@ template <bool TRACE, bool PMAX>
 static cudaError_t launch_fast(const Yaman4Params& p, bool uniform, cudaStream_t st) {
     const int  threads = kFastThreads;
     const long blocks  = (long)((p.n_points + threads - 1) / threads);
-    if (uniform)
-        yaman4_fast_kernel<TRACE, PMAX, true, kFastThreads, kFastMinBlocks><<<blocks, threads, 0, st>>>(p);
+    if (uniform && p.lossless)
+        yaman4_fast_kernel<TRACE, PMAX, 2, kFastThreads, kFastMinBlocks><<<blocks, threads, 0, st>>>(p);
+    else if (uniform)
+        yaman4_fast_kernel<TRACE, PMAX, 1, kFastThreads, kFastMinBlocks><<<blocks, threads, 0, st>>>(p);
     else
-        yaman4_fast_kernel<TRACE, PMAX, false, kFastThreads, kFastMinBlocks><<<blocks, threads, 0, st>>>(p);
+        yaman4_fast_kernel<TRACE, PMAX, 0, kFastThreads, kFastMinBlocks><<<blocks, threads, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -543,6 +560,7 @@ int yaman4_launch(const fpa_yaman4_desc* d, cudaStream_t st) {
     p.check        = (d->flags & FPA_CHECK_NAN) ? 1 : 0;
     p.n_saved      = fpa_n_saved(d->n_steps, d->save_every);
     p.coef         = make_coef(uniform ? d->gamma_uniform : 0.0, uniform ? d->alpha_uniform : 0.0, p.h);
+    p.lossless     = (uniform && d->alpha_uniform == 0.0) ? 1 : 0;
 
     cudaError_t  e;
     const int    threads = 128;
@@ -610,7 +628,10 @@ int yaman4_sweep_launch(const fpa_sweep_desc* d, cudaStream_t st) {
     p.coef       = make_coef(d->gamma / sc, d->alpha / sc, p.h);
 
     const long blocks = (long)((B + kFastThreads - 1) / kFastThreads);
-    yaman4_sweep_kernel<kFastThreads, kSweepMinBlocks><<<blocks, kFastThreads, 0, st>>>(p, x);
+    if (d->alpha == 0.0)
+        yaman4_sweep_kernel<false, kFastThreads, kSweepMinBlocks><<<blocks, kFastThreads, 0, st>>>(p, x);
+    else
+        yaman4_sweep_kernel<true, kFastThreads, kSweepMinBlocks><<<blocks, kFastThreads, 0, st>>>(p, x);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "yaman4_sweep_kernel launch");
     return FPA_OK;

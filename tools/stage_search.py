@@ -58,7 +58,7 @@ def score(orders, tag):
     cub = WORK / f"cand_{tag}.cubin"
     body = build_source(orders).replace('#include "plan_point.cuh"',
                                         f'#include "{SRC.parent}/plan_point.cuh"')
-    body += ("\nnamespace fpa { template __global__ void yaman4_fast_kernel<false, true, true, 128, 3>"
+    body += ("\nnamespace fpa { template __global__ void yaman4_fast_kernel<false, true, 1, 128, 3>"
              "(const Yaman4Params); }\n")
     # keep only the one instantiation: drop the launcher section (it instantiates everything)
     cut = body.index("// ------------------------------------------------------------------ fused sweep")
@@ -69,12 +69,12 @@ def score(orders, tag):
                         "-Xptxas", "-v", "-o", str(cub), str(src)], capture_output=True, text=True)
     if r.returncode != 0:
         return None
-    m = re.search(r"yaman4_fast_kernelILb0ELb1ELb1ELi128ELi3.*?Used (\d+) registers", r.stderr, re.S)
-    spill = re.search(r"yaman4_fast_kernelILb0ELb1ELb1ELi128ELi3.*?(\d+) bytes spill stores", r.stderr, re.S)
+    m = re.search(r"yaman4_fast_kernelILb0ELb1ELi1ELi128ELi3.*?Used (\d+) registers", r.stderr, re.S)
+    spill = re.search(r"yaman4_fast_kernelILb0ELb1ELi1ELi128ELi3.*?(\d+) bytes spill stores", r.stderr, re.S)
     regs = int(m.group(1)) if m else -1
     spills = int(spill.group(1)) if spill else -1
     out = subprocess.run([sys.executable, str(ROOT / "tools" / "sass_cost.py"), str(cub),
-                          "yaman4_fast_kernelILb0ELb1ELb1ELi128ELi3"], capture_output=True, text=True).stdout
+                          "yaman4_fast_kernelILb0ELb1ELi1ELi128ELi3"], capture_output=True, text=True).stdout
     m = re.search(r"cycles per iteration: (\d+)\s+\((\d+) instructions read 3", out)
     if not m:
         return None

@@ -35,12 +35,12 @@ float time_variant(const Yaman4Params& p, int reps) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    yaman4_fast_kernel<false, true, true, THREADS, MB><<<blocks, THREADS>>>(p);
+    yaman4_fast_kernel<false, true, 1, THREADS, MB><<<blocks, THREADS>>>(p);
     cudaDeviceSynchronize();
     float best = 1e30f;
     for (int r = 0; r < reps; ++r) {
         cudaEventRecord(e0);
-        yaman4_fast_kernel<false, true, true, THREADS, MB><<<blocks, THREADS>>>(p);
+        yaman4_fast_kernel<false, true, 1, THREADS, MB><<<blocks, THREADS>>>(p);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
@@ -55,9 +55,9 @@ float time_variant(const Yaman4Params& p, int reps) {
 template <int THREADS, int MB>
 void report(Yaman4Params p, int sms, double peak_tf) {
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, yaman4_fast_kernel<false, true, true, THREADS, MB>);
+    cudaFuncGetAttributes(&fa, yaman4_fast_kernel<false, true, 1, THREADS, MB>);
     int resident = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, yaman4_fast_kernel<false, true, true, THREADS, MB>,
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, yaman4_fast_kernel<false, true, 1, THREADS, MB>,
                                                   THREADS, 0);
     const int64_t full = p.n_points;
     const float   ms_full = time_variant<THREADS, MB>(p, 3);
