@@ -41,14 +41,14 @@ def stage(inn, base, qr, qi, cg, c2g, cn):
     Wr, Wi = fma(-qi, Ui, qr * Ur), fma(qr, Ui, qi * Ur)
     Zr, Zi = fma(qi, Vi, qr * Vr), fma(qr, Vi, -(qi * Vr))
     return [
-        fma(cn, x1, fma(-G1, y1, fma(y2, Wr, fma(-x2, Wi, base[0])))),
-        fma(cn, y1, fma(G1, x1, fma(x2, Wr, fma(y2, Wi, base[1])))),
-        fma(cn, x2, fma(-G2, y2, fma(y1, Wr, fma(-x1, Wi, base[2])))),
-        fma(cn, y2, fma(G2, x2, fma(x1, Wr, fma(y1, Wi, base[3])))),
-        fma(cn, x3, fma(-G3, y3, fma(y4, Zr, fma(-x4, Zi, base[4])))),
-        fma(cn, y3, fma(G3, x3, fma(x4, Zr, fma(y4, Zi, base[5])))),
-        fma(cn, x4, fma(-G4, y4, fma(y3, Zr, fma(-x3, Zi, base[6])))),
-        fma(cn, y4, fma(G4, x4, fma(x3, Zr, fma(y3, Zi, base[7])))),
+        fma(-G1, y1, fma(y2, Wr, fma(-x2, Wi, fma(cn, x1, base[0])))),
+        fma(G1, x1, fma(x2, Wr, fma(y2, Wi, fma(cn, y1, base[1])))),
+        fma(-G2, y2, fma(y1, Wr, fma(-x1, Wi, fma(cn, x2, base[2])))),
+        fma(G2, x2, fma(x1, Wr, fma(y1, Wi, fma(cn, y2, base[3])))),
+        fma(-G3, y3, fma(y4, Zr, fma(-x4, Zi, fma(cn, x3, base[4])))),
+        fma(G3, x3, fma(x4, Zr, fma(y4, Zi, fma(cn, y3, base[5])))),
+        fma(-G4, y4, fma(y3, Zr, fma(-x3, Zi, fma(cn, x4, base[6])))),
+        fma(G4, x4, fma(x3, Zr, fma(y3, Zi, fma(cn, y4, base[7])))),
     ]
 
 

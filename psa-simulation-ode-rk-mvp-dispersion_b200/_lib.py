@@ -6,6 +6,7 @@ device is visible, every compute call raises.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from pathlib import Path
@@ -134,6 +135,15 @@ class FpaError(RuntimeError):
     """CUDA / device failure reported by libfpa_b200."""
 
 
+def _load(path: Path):
+    handle = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    return handle
+
+
 def lib():
     """Load (once) and return the shared library; raises if it has not been built."""
     global _lib
@@ -144,13 +154,22 @@ def lib():
                 f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a).  This package has no CPU fallback."
             )
-        handle = C.CDLL(str(path))
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(handle, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = handle
+        _lib = _load(path)
     return _lib
+
+
+@contextlib.contextmanager
+def use_library(path):
+    """Route every call of this package through another build of the same C ABI for the duration
+    of the block (tests: the library with ptxas' own instruction schedule, build/libfpa_b200_ref.so,
+    must give bit-identical results)."""
+    global _lib
+    saved = lib()
+    _lib = _load(Path(path))
+    try:
+        yield _lib
+    finally:
+        _lib = saved
 
 
 def last_error() -> str:

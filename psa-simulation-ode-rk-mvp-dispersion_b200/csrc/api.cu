@@ -172,7 +172,13 @@ using namespace fpa;
 extern "C" {
 
 const char* fpa_last_error(void) { return g_err; }
-const char* fpa_version(void) { return "fpa_b200 0.1 (sm_100a)"; }
+const char* fpa_version(void) {
+#if defined(FPA_SASS_PASS) && FPA_SASS_PASS
+    return "fpa_b200 0.2 (sm_100a; FP64 hot loops re-scheduled after ptxas: tools/sass_sched.py)";
+#else
+    return "fpa_b200 0.2 (sm_100a; ptxas schedule)";
+#endif
+}
 
 int fpa_device_count(void) {
     int n = 0;

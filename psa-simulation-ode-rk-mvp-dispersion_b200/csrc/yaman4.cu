@@ -105,15 +105,17 @@ __device__ __forceinline__ void stage(const double (&in)[8], const double (&base
     const double Zr = fma(qi, Vi, qr * Vr),  Zi = fma(qr, Vi, -(qi * Vr));
     // out_j = base_j + cn*A_j + i*G_j*A_j + i*conj(A_m)*{W|Z}
     //   i*conj(A_m)*W = (ym Wr - xm Wi) + i (xm Wr + ym Wi)
+    // The loss term is added FIRST: it needs nothing but the stage input, so the SASS pass
+    // (tools/sass_sched.py) can issue it right before an FMA that shares its operand.
     if (LOSS) {
-        out[0] = fma(cn, x1, fma(-G1, y1, fma(y2, Wr, fma(-x2, Wi, base[0]))));
-        out[1] = fma(cn, y1, fma(G1, x1, fma(x2, Wr, fma(y2, Wi, base[1]))));
-        out[2] = fma(cn, x2, fma(-G2, y2, fma(y1, Wr, fma(-x1, Wi, base[2]))));
-        out[3] = fma(cn, y2, fma(G2, x2, fma(x1, Wr, fma(y1, Wi, base[3]))));
-        out[4] = fma(cn, x3, fma(-G3, y3, fma(y4, Zr, fma(-x4, Zi, base[4]))));
-        out[5] = fma(cn, y3, fma(G3, x3, fma(x4, Zr, fma(y4, Zi, base[5]))));
-        out[6] = fma(cn, x4, fma(-G4, y4, fma(y3, Zr, fma(-x3, Zi, base[6]))));
-        out[7] = fma(cn, y4, fma(G4, x4, fma(x3, Zr, fma(y3, Zi, base[7]))));
+        out[0] = fma(-G1, y1, fma(y2, Wr, fma(-x2, Wi, fma(cn, x1, base[0]))));
+        out[1] = fma(G1, x1, fma(x2, Wr, fma(y2, Wi, fma(cn, y1, base[1]))));
+        out[2] = fma(-G2, y2, fma(y1, Wr, fma(-x1, Wi, fma(cn, x2, base[2]))));
+        out[3] = fma(G2, x2, fma(x1, Wr, fma(y1, Wi, fma(cn, y2, base[3]))));
+        out[4] = fma(-G3, y3, fma(y4, Zr, fma(-x4, Zi, fma(cn, x3, base[4]))));
+        out[5] = fma(G3, x3, fma(x4, Zr, fma(y4, Zi, fma(cn, y3, base[5]))));
+        out[6] = fma(-G4, y4, fma(y3, Zr, fma(-x3, Zi, fma(cn, x4, base[6]))));
+        out[7] = fma(G4, x4, fma(x3, Zr, fma(y3, Zi, fma(cn, y4, base[7]))));
     } else {  // alpha == 0: the reference's loss term is exact zeros (yaman_model.py:129-130)
         out[0] = fma(-G1, y1, fma(y2, Wr, fma(-x2, Wi, base[0])));
         out[1] = fma(G1, x1, fma(x2, Wr, fma(y2, Wi, base[1])));

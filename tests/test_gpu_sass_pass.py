@@ -1,0 +1,83 @@
+"""GPU: the library whose FP64 hot loops were re-scheduled after ptxas (tools/sass_sched.py) must
+give results BIT-IDENTICAL to the same sources with ptxas' own schedule
+(build/libfpa_b200_ref.so).  The pass only re-orders instructions, swaps commutative operands and
+sets operand-reuse flags, so any differing bit is a scheduling hazard."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(gpu, fn):
+    out = fn()
+    if not entry.REF_LIB.exists():
+        pytest.fail("build/libfpa_b200_ref.so missing: build() did not produce the reference-schedule library")
+    with gpu._lib.use_library(entry.REF_LIB) as ref:
+        assert b"ptxas schedule" in ref.fpa_version()
+        out_ref = fn()
+    return out, out_ref
+
+
+def _same(a, b):
+    for k in a:
+        if isinstance(a[k], np.ndarray):
+            assert a[k].tobytes() == b[k].tobytes(), f"{k} differs between the two schedules"
+
+
+def test_shipped_library_carries_the_pass(gpu):
+    assert b"re-scheduled after ptxas" in gpu._lib.lib().fpa_version()
+
+
+@pytest.mark.parametrize("alpha", [0.0, 1.15e-4])
+def test_fused_sweep_bit_identical(gpu, golden, alpha):
+    b2, b3, b4, wref = golden["b4_beta"]
+    cfg = gpu.config.custom_simulation_config(z_max=100.0, dz=0.2, save_every=10)
+    lam1 = np.linspace(1545e-9, 1555e-9, 64)
+    lam3 = np.linspace(1540e-9, 1565e-9, 1000)
+    disp = gpu.dispersion.DispersionParams(omega_ref=wref, beta2=b2, beta3=b3, beta4=b4)
+    run = lambda: gpu.scan_mismtach.sweep_gain_2d(  # noqa: E731
+        cfg=cfg, lambda_p1_m=lam1, lambda_signal_m=lam3, lambda_p2_m=1558e-9, gamma=11.5e-3, alpha=alpha,
+        p_in=golden["b4_p_in"], dispersion=disp, gain_unit="linear")
+    a, b = _both(gpu, run)
+    _same(a, b)
+    assert np.isfinite(a["gain"]).all()
+
+
+@pytest.mark.parametrize("outputs", [("end", "pmax"), ("trace",), ("end",), ("trace", "end", "pmax")])
+@pytest.mark.parametrize("uniform", [True, False])
+@pytest.mark.parametrize("alpha", [0.0, 2e-4])
+def test_batch_integrator_bit_identical(gpu, outputs, uniform, alpha):
+    """Every instantiation of the fast kernel: TRACE/PMAX x {uniform, lossless, per-point physics}."""
+    cfg = gpu.config.custom_simulation_config(z_max=300.0, dz=0.25, save_every=7)
+    rng = np.random.default_rng(5)
+    B = 20_000
+    db = rng.normal(size=B) * 0.02
+    gamma = 11.5e-3 if uniform else rng.uniform(5e-3, 2e-2, B)
+    al = alpha if uniform else np.full(B, alpha)
+    run = lambda: gpu.simulation.run_batch_simulation(  # noqa: E731
+        cfg, gamma=gamma, alpha=al, delta_beta=db, p_in=[0.3, 0.2, 1e-4, 1e-6], outputs=outputs)
+    a, b = _both(gpu, run)
+    _same(a, b)
+
+
+@pytest.mark.parametrize("grid", [False, True])
+def test_exact_phase_kernel_bit_identical(gpu, grid):
+    rng = np.random.default_rng(6)
+    B = 4096
+    db = rng.normal(size=B) * 0.05
+    if grid:
+        z = np.cumsum(np.concatenate(([0.0], rng.uniform(0.05, 0.3, 400))))
+        A0 = np.tile(np.sqrt(np.array([0.3, 0.2, 1e-4, 1e-6])).astype(complex), (B, 1))
+        run = lambda: gpu._device.yaman4_batch(  # noqa: E731
+            db, np.asarray(11.5e-3), np.asarray(2e-4), A0, z_max=float(z[-1]), n_steps=z.size - 1, z_grid=z,
+            save_every=5, trace=True, end=True,
+            pmax=True, check_nan=True, phase_exact=True)
+    else:
+        cfg = gpu.config.custom_simulation_config(z_max=100.0, dz=0.25, save_every=5)
+        run = lambda: gpu.simulation.run_batch_simulation(  # noqa: E731
+            cfg, gamma=11.5e-3, alpha=2e-4, delta_beta=db, p_in=[0.3, 0.2, 1e-4, 1e-6],
+            outputs=("end", "pmax", "trace"), phase_exact=True)
+    a, b = _both(gpu, run)
+    _same(a, b)
