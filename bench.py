@@ -49,9 +49,9 @@ P_IN = [0.1, 0.1, 1e-7, 1e-7]
 LAM_P2 = 1558e-9
 FLOPS_PER_POINT_STEP = 568.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused sweep kernel on this workload,
-# from the committed ncu capture (cannot be measured outside a profiler): 81.9 KB read + 0 B written --
+# from the committed ncu capture (cannot be measured outside a profiler): 116 KB read + 0 B written --
 # the 24 MB of per-point results are still in the 126 MB L2 when the kernel ends
-NCU_DRAM_BYTES_PER_LAUNCH = 81920.0
+NCU_DRAM_BYTES_PER_LAUNCH = 115968.0
 
 
 def workload_axes(rank: int, world: int, scaling: str = "weak"):
@@ -119,7 +119,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_points = 2 * cores
+    n_points = 16 * cores            # a few seconds of all-core work per bench step
     n_steps = int(round(Z_MAX / DZ))
     for _ in range(max(args.warmup, 0)):
         cpu_sample(cores, cores, seed=99)
@@ -252,10 +252,17 @@ def run_ours(args) -> None:
     d.gain_lin, d.status, d.Pmax, d.A_end = t_gain.data_ptr(), t_status.data_ptr(), None, None
     launches_per_step = 1        # yaman4_sweep_kernel: plan + dbeta prologue, fused RK4 loop, gain epilogue
 
+    # CUDA events around every launch of the sweep kernel, on the stream it is launched on
+    k_events = []
+
     def step():
         t_flush.zero_()                                                    # L2 flush between steps
         stream = torch.cuda.current_stream().cuda_stream
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
         L.check(lib.fpa_yaman4_sweep_dev(C.byref(d), t_scratch.data_ptr(), scratch_bytes, stream))
+        k1.record()
+        k_events.append((k0, k1))
         if world > 1 and t_all is not None:
             dist.all_gather_into_tensor(t_all, t_gain)                     # the final result gather
         elif world > 1:                                                    # strong scaling: ragged row blocks
@@ -289,29 +296,8 @@ def run_ours(args) -> None:
         ms_total = float(t.item())
     value = total_points * n_steps * args.steps / (ms_total * 1e-3)
 
-    # ---- the RK4 integrator alone (no plan prologue / gain epilogue), for the roofline
-    yd = L.Yaman4Desc()
-    consts = torch.tensor([GAMMA, ALPHA] + [v for a in A0 for v in (a.real, a.imag)], dtype=torch.float64, device=dev)
-    t_pmax = torch.empty(B * 4, dtype=torch.float64, device=dev)
-    yd.n_points = B
-    yd.dbeta = t_dbeta.data_ptr()
-    yd.gamma, yd.gamma_stride = consts.data_ptr(), 0
-    yd.alpha, yd.alpha_stride = consts.data_ptr() + 8, 0
-    yd.A0, yd.A0_stride = consts.data_ptr() + 16, 0
-    yd.z0, yd.z_max, yd.n_steps, yd.save_every = 0.0, Z_MAX, n_steps, SAVE_EVERY
-    yd.flags = L.OUT_PMAX | L.CHECK_NAN | L.UNIFORM_PHYSICS
-    yd.gamma_uniform, yd.alpha_uniform = GAMMA, ALPHA
-    yd.Pmax, yd.status = t_pmax.data_ptr(), t_status.data_ptr()
-    k_ms = []
-    for it in range(2 + 3):
-        t_flush.zero_()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        L.check(lib.fpa_yaman4_rk4_batch_dev(C.byref(yd), torch.cuda.current_stream().cuda_stream))
-        k1.record()
-        torch.cuda.synchronize()
-        if it >= 2:
-            k_ms.append(k0.elapsed_time(k1))
+    # ---- roofline: the launches of the timed region themselves (warm-up launches dropped)
+    k_ms = [k0.elapsed_time(k1) for k0, k1 in k_events[-args.steps:]]
     kernel_ms = float(np.mean(k_ms))
     achieved_tf = FLOPS_PER_POINT_STEP * B * n_steps / (kernel_ms * 1e-3) / 1e12
 
@@ -376,13 +362,16 @@ def run_ours(args) -> None:
                    "l2": "256 MiB buffer written between steps (inside the timed region); "
                          "the kernel keeps its state in registers"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "scan_mismtach.sweep_gain_2d -> fpa_yaman4_sweep_host, pinned host buffers"},
+                "steps": e2e_steps, "api": "scan_mismtach.sweep_gain_2d -> fpa_yaman4_sweep_host; axes copied up from pinned host memory, the "
+                       "kernel writes its 24 B per point straight into the pinned host result buffers"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/r1_ncu_yaman4_sweep_kernel.csv)",
-                     "kernel": "yaman4_fast_kernel<PMAX,UNIFORM> (the z-loop the fused yaman4_sweep_kernel runs)", "kernel_ms": kernel_ms,
+                     "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/r1_ncu_yaman4_sweep_kernel_sass.csv)",
+                     "kernel": "yaman4_sweep_kernel<LOSS,128,4> (plan + dbeta prologue, fused RK4 z-loop, gain epilogue; "
+                               "every launch of the timed region, CUDA events on the launching stream)",
+                     "kernel_ms": kernel_ms, "library": lib.fpa_version().decode(),
                      "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
                      "flops_per_point_step": FLOPS_PER_POINT_STEP,
                      "peak_source": "DFMA probe measured live on this GPU (fpa_fp64_peak_probe); "
@@ -393,7 +382,7 @@ def run_ours(args) -> None:
     }
     if world == 1 and not args.no_cpu_baseline and args.scaling == "weak":
         cores = os.cpu_count() or 1
-        n_pts = max(16, 2 * cores)
+        n_pts = max(64, 40 * cores)      # ~10 s of wall time on the box's cores
         cpu_value, wall, idx, cpu_gain = cpu_sample(n_pts, cores, seed=0)
         gpu_gain = gain_dev.reshape(-1)[idx]
         out["cpu_baseline"] = {

@@ -112,6 +112,21 @@ static int down(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     return FPA_OK;
 }
 
+// Address at which a kernel can write `host_ptr` directly (pinned / registered host memory under
+// unified addressing), or nullptr for pageable memory.  The reduce-mode sweep writes its 24 bytes
+// per scan point straight into such buffers while it runs: no staging copy after the kernel.
+template <typename T>
+static T* mapped(T* host_ptr) {
+    if (host_ptr == nullptr) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+    return static_cast<T*>(at.devicePointer);
+}
+
 #define FPA_TRY(expr)                  \
     do {                               \
         int rc__ = (expr);             \
@@ -438,25 +453,34 @@ int fpa_yaman4_sweep_host(const fpa_sweep_desc* d, int device) {
     FPA_TRY(up(l1, pl.lambda1, n1 * 8, st));
     FPA_TRY(up(l2, pl.lambda2, n2 * 8, st));
     FPA_TRY(up(l3, pl.lambda3, n3 * 8, st));
+    // Outputs in pinned host memory are written by the kernel itself (each thread stores its
+    // results when it finishes, so the PCIe traffic hides behind the integration of the other
+    // points); pageable outputs go through the device workspace and a copy.
+    double*  m_gain = mapped(d->gain_lin);
+    double*  m_db   = mapped(pl.dbeta);
+    int32_t* m_va   = mapped(pl.valid);
+    int32_t* m_st   = mapped(d->status);
+    double*  m_Pm   = mapped(d->Pmax);
+    double*  m_Ae   = mapped(d->A_end);
     fpa_sweep_desc dd = *d;
     dd.plan.lambda1 = l1;
     dd.plan.lambda2 = l2;
     dd.plan.lambda3 = l3;
     dd.plan.omega   = pl.omega ? om : nullptr;
-    dd.plan.dbeta   = db;
-    dd.plan.valid   = va;
-    dd.gain_lin     = gain;
-    dd.Pmax         = d->Pmax ? Pm : nullptr;
-    dd.A_end        = d->A_end ? Ae : nullptr;
-    dd.status       = stt;
+    dd.plan.dbeta   = m_db ? m_db : db;
+    dd.plan.valid   = m_va ? m_va : va;
+    dd.gain_lin     = m_gain ? m_gain : gain;
+    dd.Pmax         = d->Pmax ? (m_Pm ? m_Pm : Pm) : nullptr;
+    dd.A_end        = d->A_end ? (m_Ae ? m_Ae : Ae) : nullptr;
+    dd.status       = m_st ? m_st : stt;
     FPA_TRY(sweep_dev(&dd, st));
-    FPA_TRY(down(d->gain_lin, gain, B * 8, st));
-    FPA_TRY(down(pl.dbeta, db, B * 8, st));
-    FPA_TRY(down(pl.valid, va, B * 4, st));
+    if (!m_gain) FPA_TRY(down(d->gain_lin, gain, B * 8, st));
+    if (!m_db) FPA_TRY(down(pl.dbeta, db, B * 8, st));
+    if (!m_va) FPA_TRY(down(pl.valid, va, B * 4, st));
     FPA_TRY(down(pl.omega, om, B * 32, st));
-    FPA_TRY(down(d->status, stt, B * 4, st));
-    FPA_TRY(down(d->Pmax, Pm, B * 32, st));
-    FPA_TRY(down(d->A_end, Ae, B * 64, st));
+    if (!m_st) FPA_TRY(down(d->status, stt, B * 4, st));
+    if (!m_Pm) FPA_TRY(down(d->Pmax, Pm, B * 32, st));
+    if (!m_Ae) FPA_TRY(down(d->A_end, Ae, B * 64, st));
     FPA_CUDA(cudaStreamSynchronize(st));
     return FPA_OK;
 }

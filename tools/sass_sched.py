@@ -646,18 +646,30 @@ class BlockScheduler:
         fp = [j for j in range(n) if self.seq[j].is_fp64]
         for it in range(iters):
             temp = t_start * (t_end / t_start) ** (it / max(1, iters - 1))
-            j = fp[int(rng.random() * len(fp))]
-            pos = {q: k for k, q in enumerate(order)}
-            lo = max([pos[i] for i in pred_set[j]], default=-1) + 1
-            hi = min([pos[k] for k in succ_set[j]], default=n) - 1   # last position j may take
-            c = pos[j]
-            if hi <= lo:
-                continue
-            q = lo + int(rng.random() * (hi - lo + 1))
-            if q == c:
-                continue
-            trial = order[:c] + order[c + 1:]
-            trial.insert(q, j)
+            if rng.random() < 0.5:
+                # move one FP64 instruction anywhere between its last predecessor and first successor
+                j = fp[int(rng.random() * len(fp))]
+                pos = {q: k for k, q in enumerate(order)}
+                lo = max([pos[i] for i in pred_set[j]], default=-1) + 1
+                hi = min([pos[k] for k in succ_set[j]], default=n) - 1   # last position j may take
+                c = pos[j]
+                if hi <= lo:
+                    continue
+                q = lo + int(rng.random() * (hi - lo + 1))
+                if q == c:
+                    continue
+                trial = order[:c] + order[c + 1:]
+                trial.insert(q, j)
+            else:
+                # move a short run of consecutive instructions (a reuse chain) as a whole
+                ln = 2 + int(rng.random() * 4)
+                c = int(rng.random() * (n - ln))
+                seg = order[c:c + ln]
+                rest = order[:c] + order[c + ln:]
+                q = max(0, min(len(rest), c + int((rng.random() - 0.5) * 80)))
+                if q == c:
+                    continue
+                trial = rest[:q] + seg + rest[q:]
             r = self.evaluate(trial)
             if r is None:
                 continue

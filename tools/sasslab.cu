@@ -9,6 +9,7 @@
 // run:          tools/sasslab.bin <kernel-name> a.cubin [b.cubin ...]
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -112,13 +113,14 @@ int main(int argc, char** argv) {
         int regs = 0;
         cuFuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn);
         void*          args[] = {&p};
-        const unsigned blocks = (unsigned)((B + 127) / 128);
+        const unsigned threads = getenv("LAB_THREADS") ? (unsigned)atoi(getenv("LAB_THREADS")) : 128u;
+        const unsigned blocks = (unsigned)((B + threads - 1) / threads);
         cudaMemset(d_pmax, 0, B * 32);
         cudaMemset(d_end, 0, B * 64);
         float best = 1e30f;
         for (int r = 0; r < 4; ++r) {
             cudaEventRecord(e0);
-            CU(cuLaunchKernel(fn, blocks, 1, 1, 128, 1, 1, 0, 0, args, nullptr));
+            CU(cuLaunchKernel(fn, blocks, 1, 1, threads, 1, 1, 0, 0, args, nullptr));
             cudaEventRecord(e1);
             if (cudaEventSynchronize(e1) != cudaSuccess) {
                 fprintf(stderr, "%s: kernel failed: %s\n", argv[a], cudaGetErrorString(cudaGetLastError()));
