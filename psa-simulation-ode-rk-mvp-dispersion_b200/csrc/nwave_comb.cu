@@ -1,24 +1,30 @@
-// nwave_comb.cu -- N-wave RK4 for plans on an integer frequency grid, in convolution form
+// nwave_comb.cu -- N-wave RK4 for plans on an integer frequency grid, in correlation form
 // (NOT in the reference; SURVEY App. C "uniform-comb shortcut").
 //
 // On a grid w_j = w_0 + g_j*dw the matching condition w_k + w_l - w_m = w_n is g_k + g_l - g_m = g_n,
-// so with At_j = A_j exp(i*beta_j*z) placed at grid slot g_j - g_min (empty slots hold 0):
+// so with At_j = A_j exp(i*beta_j*z) placed at grid slot g_j - g_min (empty slots hold 0) the whole
+// FWM + SPM + XPM sum of wave n is
 //
-//     sum over ordered (k,l) and all m of At_k At_l conj(At_m)  =  sum_m conj(At_m) * C_{n+m},
-//     C_s = sum_{k+l=s} At_k At_l                                   (auto-convolution)
+//     R_n = sum_{k,l,m : k+l-m=n} At_k At_l conj(At_m) = sum_k At_k * X_{n-k},
+//     X_d = sum_m At_{m+d} conj(At_m)            (auto-correlation, X_{-d} = conj(X_d))
 //
-// which is O(M^2) per RHS (M = grid span) instead of O(N^3) table entries, and contains the SPM/XPM
-// terms (m = k or m = l) with exactly the weights of the analytic Kerr factor (2*sum P - P_n), so
+// i.e. one correlation and one convolution of length-M sequences (M = grid span): 2*M^2 complex
+// MACs per RHS instead of O(N^3) table entries, with exactly the weights of the analytic Kerr
+// factor (2*sum P - P_n) for the m = k / m = l terms, and
 //
-//     dA_n/dz = -(alpha/2) A_n + i*gamma * conj(E_n) * sum_m conj(At_m) C_{n+m} .
+//     dA_n/dz = -(alpha/2) A_n + i*gamma * conj(E_n) * R_n ,   E_n = exp(i*beta_n*z).
 //
-// It is the same ODE as nwave.cu integrates from the enumerated triplet table (tests compare both
-// with the oracle); N = 64 needs 2*64^2 complex MACs per RHS instead of 84 320 table entries.
+// Same ODE as nwave.cu integrates from the enumerated triplet table (tests compare both with the
+// oracle).  Both sums have the shape  out[o] = sum_i a[i] * w[i + o]:  a thread owns a TILE of
+// adjacent outputs and a contiguous part of the i-range, keeps the TILE accumulators and a sliding
+// window of w in registers (one new shared-memory word and one broadcast per TILE complex MACs --
+// the FP64 pipe is the limiter, not the LSU), and the parts are combined with warp shuffles.
 //
-// Mapping: one CTA per scan point, everything in shared memory for all z-steps; thread s owns C_s
-// (the k-sum uses the k<->l symmetry: half the terms, doubled), thread j owns wave j's correlation
-// sum and its RK4 update.  Neighbouring threads read neighbouring shared-memory words (C_{n+m},
-// At_{s-k}) and the common operand is a broadcast.
+// Two mappings of the same code (template parameter W = warps per scan point):
+//   W = 1  one warp per point, 8 points per CTA, __syncwarp only: throughput for large batches;
+//   W = 8  one CTA per point, sums split 8 ways: latency for single runs / small batches.
+// exp(i*beta_n*z) advances by a constant rotation per half step (exact sincos every kResync steps),
+// the step is the constant h = (z_max - z0)/n_steps like the 4-wave fast kernel.
 #include "fpa_common.cuh"
 
 namespace fpa {
@@ -42,12 +48,30 @@ struct CombParams {
     int            check;
 };
 
+constexpr int kCombThreads = 256;
+constexpr int kCombResync  = 32;
+constexpr int kPad         = 8;  // spare words of R
+
 struct CombSmem {
-    double2 *y, *ys, *yn, *E, *At, *C;
+    double2 *y, *ys, *yn, *E, *Eh, *rot;  // [N] state, stage state, accumulator, phases
+    double2 *At;                          // [seq_words]  At on the grid at padx(slot), zeros above M
+    double2 *Y;                           // [seq_words]  Y[padx(q)] = X_{M-1-q}, zeros above 2M-2
+    double2 *R;                           // [M + kPad]
     double*  beta;
     int*     slot;
-    int*     flag;
 };
+
+// words of a zero-padded, bank-skewed sequence buffer (At and Y): the sums run over whole blocks of 8
+// terms per part (at most 8 parts), so indices reach 2*roundup(M, 64) + 16
+__host__ __device__ inline int comb_seq_words(int M) {
+    const int e = 2 * ((M + 63) & ~63) + 16;
+    return e + (e >> 2) + 1;
+}
+
+__host__ __device__ inline size_t comb_point_doubles(int N, int M) {
+    const size_t d = 2 * (size_t)(6 * N + 2 * comb_seq_words(M) + (M + kPad)) + (size_t)N + (size_t)(N + 1) / 2 + 2;
+    return (d + 1) & ~(size_t)1;  // keeps every point's block 16-byte aligned
+}
 
 __device__ __forceinline__ CombSmem comb_carve(double* base, int N, int M) {
     CombSmem s;
@@ -55,147 +79,231 @@ __device__ __forceinline__ CombSmem comb_carve(double* base, int N, int M) {
     s.ys   = s.y + N;
     s.yn   = s.ys + N;
     s.E    = s.yn + N;
-    s.At   = s.E + N;
-    s.C    = s.At + M;
-    s.beta = reinterpret_cast<double*>(s.C + (2 * M - 1));
+    s.Eh   = s.E + N;
+    s.rot  = s.Eh + N;
+    s.At   = s.rot + N;
+    s.Y    = s.At + comb_seq_words(M);
+    s.R    = s.Y + comb_seq_words(M);
+    s.beta = reinterpret_cast<double*>(s.R + (M + kPad));
     s.slot = reinterpret_cast<int*>(s.beta + N);
-    s.flag = s.slot + N;
     return s;
 }
 
-static size_t comb_smem_bytes(int N, int M) {
-    return sizeof(double2) * (size_t)(4 * N + M + 2 * M - 1) + sizeof(double) * (size_t)N +
-           sizeof(int) * (size_t)(N + 2);
+template <int W>
+__device__ __forceinline__ void comb_sync() {
+    if (W == 1)
+        __syncwarp();
+    else
+        __syncthreads();
 }
 
-// One RHS evaluation at z on the stage state s.ys, then for every wave the RK4 bookkeeping:
-//   yn += wa*k ; ys = y + wb*k            (or y = yn + wa*k when `last`)
-__device__ void comb_stage(const CombSmem& s, const CombParams& p, double z, double gamma, double nha,
-                           double wa, double wb, bool last, bool first_of_run_check, int& nonfinite_seen) {
-    const int N = p.n_waves, M = p.span, tid = threadIdx.x, nt = blockDim.x;
+// Shared-memory position of sequence element e: one spare word after every four, so that the
+// windows of eight neighbouring TILE = 4 tiles (16-byte words 4 apart) fall into distinct banks.
+__host__ __device__ __forceinline__ int padx(int e) { return e + (e >> 2); }
 
-    for (int j = tid; j < N; j += nt) {
-        double sn, cs;
-        sincos(s.beta[j] * z, &sn, &cs);
-        const double2 a = s.ys[j];
-        s.E[j] = make_double2(cs, sn);
-        s.At[s.slot[j]] = make_double2(fma(-a.y, sn, a.x * cs), fma(a.x, sn, a.y * cs));
-        if (first_of_run_check && (nonfinite(a.x) || nonfinite(a.y))) nonfinite_seen = 1;
-    }
-    __syncthreads();
-
-    // C_s = sum_{k+l=s} At_k At_l = 2*sum_{k<l} + [s even] At_{s/2}^2
-    for (int sidx = tid; sidx < 2 * M - 1; sidx += nt) {
-        const int klo = sidx - (M - 1) > 0 ? sidx - (M - 1) : 0;
-        const int khi = (sidx - 1) >> 1;  // largest k with k < s-k
-        double cr = 0.0, ci = 0.0;
-        for (int k = klo; k <= khi; ++k) {
-            const double2 a = s.At[k], b = s.At[sidx - k];
-            cr = fma(a.x, b.x, fma(-a.y, b.y, cr));
-            ci = fma(a.x, b.y, fma(a.y, b.x, ci));
-        }
-        cr += cr;
-        ci += ci;
-        if ((sidx & 1) == 0) {
-            const double2 a = s.At[sidx >> 1];
-            cr = fma(a.x, a.x, fma(-a.y, a.y, cr));
-            ci = fma(a.x + a.x, a.y, ci);
-        }
-        s.C[sidx] = make_double2(cr, ci);
-    }
-    __syncthreads();
-
-    for (int j = tid; j < N; j += nt) {
-        const int n = s.slot[j];
-        double rr = 0.0, ri = 0.0;
-        for (int m = 0; m < M; ++m) {
-            const double2 a = s.At[m], c = s.C[n + m];
-            // conj(a) * c
-            rr = fma(a.x, c.x, fma(a.y, c.y, rr));
-            ri = fma(a.x, c.y, fma(-a.y, c.x, ri));
-        }
-        const double2 e = s.E[j], x = s.ys[j];
-        // F = conj(E_n) * R ;  k = nha*x + i*gamma*F
-        const double fr = fma(ri, e.y, rr * e.x);
-        const double fi = fma(ri, e.x, -(rr * e.y));
-        const double kr = fma(nha, x.x, -(gamma * fi));
-        const double ki = fma(nha, x.y, gamma * fr);
-        if (last) {
-            const double2 acc = s.yn[j];
-            s.y[j] = make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y));
-        } else {
-            const double2 y0 = s.y[j], acc = s.yn[j];
-            s.yn[j] = make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y));
-            s.ys[j] = make_double2(fma(wb, kr, y0.x), fma(wb, ki, y0.y));
+// acc[t] += a[i] (x) w[wbase + i + t]  for i in [i0, i1), t in [0, TILE);  (x) = conj(a)*w when CONJ
+// else a*w.  i0 and i1 are multiples of 8 (and wbase of 4 when TILE = 4), so inside a block of K = 8
+// terms every operand sits at a fixed offset from two base addresses; all operands of a block are loaded first
+// (independent loads in flight together), then K*TILE complex MACs run from registers.  No bounds
+// tests: the sequences are zero beyond their last element.
+template <bool CONJ, int TILE>
+__device__ __forceinline__ void sliding_mac(const double2* __restrict__ a, const double2* __restrict__ w, int wbase,
+                                            int i0, int i1, double (&re)[TILE], double (&im)[TILE]) {
+    constexpr int K = 8;
+    for (int i = i0; i < i1; i += K) {
+        const double2* ap = a + padx(i);
+        const double2* wp = w + padx(wbase + i);
+        const int      ph = (TILE % 4 == 0) ? 0 : ((wbase + i) & 3);  // position inside the group of four
+        double2 av[K], wv[K + TILE - 1];
+#pragma unroll
+        for (int k = 0; k < K; ++k) av[k] = ap[k + (k >> 2)];
+#pragma unroll
+        for (int k = 0; k < K + TILE - 1; ++k) wv[k] = wp[k + ((ph + k) >> 2)];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int t = 0; t < TILE; ++t) {
+                if (CONJ) {  // conj(a) * w
+                    re[t] = fma(av[k].x, wv[k + t].x, fma(av[k].y, wv[k + t].y, re[t]));
+                    im[t] = fma(av[k].x, wv[k + t].y, fma(-av[k].y, wv[k + t].x, im[t]));
+                } else {     // a * w
+                    re[t] = fma(av[k].x, wv[k + t].x, fma(-av[k].y, wv[k + t].y, re[t]));
+                    im[t] = fma(av[k].x, wv[k + t].y, fma(av[k].y, wv[k + t].x, im[t]));
+                }
+            }
         }
     }
-    __syncthreads();
 }
 
-__global__ void nwave_comb_kernel(const CombParams p) {
-    extern __shared__ double comb_smem_raw[];
-    const int     N = p.n_waves, M = p.span, tid = threadIdx.x, nt = blockDim.x;
-    const int64_t b = blockIdx.x;
-    CombSmem      s = comb_carve(comb_smem_raw, N, M);
+// out[o] = sum_{i<M} a[i] (x) w[i + o] for o in [0, n_out): tiles of TILE outputs; the i-range is
+// split into SPLIT contiguous parts held by lanes LP = 32/SPLIT apart in the same warp (so the
+// eight lanes of a shared-memory wavefront work on eight neighbouring tiles of one part), combined
+// by shuffles; the part-0 lane calls store(o, re, im).  W warps share the tiles of one point.
+template <bool CONJ, int TILE, int SPLIT, int W, typename Store>
+__device__ __forceinline__ void tiled_correlation(const double2* a, const double2* w, int M, int n_out, int tid,
+                                                  Store store) {
+    constexpr int LP = 32 / SPLIT;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int part = lane / LP, tl = lane % LP;
+    const int n_tiles = (n_out + TILE - 1) / TILE;
+    const int chunk   = ((M + SPLIT - 1) / SPLIT + 7) & ~7;  // whole blocks of 8 terms; the tail reads zeros
+    const int i0      = part * chunk;
+    const int i1      = i0 + chunk;
+    // every lane of a warp runs the same number of rounds (the shuffles below need all of them)
+    const int rounds = (n_tiles + W * LP - 1) / (W * LP);
+    for (int r = 0; r < rounds; ++r) {
+        const int  tile = (r * W + warp) * LP + tl;
+        const bool live = tile < n_tiles;
+        double     re[TILE], im[TILE];
+#pragma unroll
+        for (int t = 0; t < TILE; ++t) re[t] = im[t] = 0.0;
+        if (live) sliding_mac<CONJ, TILE>(a, w, tile * TILE, i0, i1, re, im);
+#pragma unroll
+        for (int d = LP; d < 32; d <<= 1) {
+#pragma unroll
+            for (int t = 0; t < TILE; ++t) {
+                re[t] += __shfl_xor_sync(0xffffffffu, re[t], d);
+                im[t] += __shfl_xor_sync(0xffffffffu, im[t], d);
+            }
+        }
+        if (live && part == 0) {
+#pragma unroll
+            for (int t = 0; t < TILE; ++t)
+                if (tile * TILE + t < n_out) store(tile * TILE + t, re[t], im[t]);
+        }
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kCombThreads) nwave_comb_kernel(const CombParams p) {
+    constexpr int T     = 32 * W;            // threads per scan point
+    constexpr int PPC   = kCombThreads / T;  // points per CTA
+    constexpr int TILE  = W == 1 ? 4 : 2;
+    constexpr int SPLIT = W == 1 ? 2 : 8;
+    extern __shared__ __align__(16) double comb_smem_raw[];
+    const int     N = p.n_waves, M = p.span;
+    const int     sub = threadIdx.x / T, tid = threadIdx.x % T;
+    const int64_t b = (int64_t)blockIdx.x * PPC + sub;
+    if (b >= p.n_points) return;  // W = 1: whole warps leave; W = 8: PPC = 1, never taken
+    CombSmem s = comb_carve(comb_smem_raw + (size_t)sub * comb_point_doubles(N, M), N, M);
 
     const double gamma = p.gamma[b * p.gamma_stride];
     const double nha   = -0.5 * p.alpha[b * p.alpha_stride];
-    for (int j = tid; j < N; j += nt) {
-        s.beta[j] = p.beta[b * p.beta_stride * N + j];
+    const int    n_steps = p.n_steps;
+    const double z0 = p.z0;
+    const double h = (p.z_max - z0) / (double)n_steps, hh = 0.5 * h, h6 = h / 6.0, h3 = h6 + h6;
+
+    for (int j = tid; j < N; j += T) {
+        const double bj = p.beta[b * p.beta_stride * N + j];
+        s.beta[j] = bj;
         s.slot[j] = p.slot[j];
         const double2* a0 = reinterpret_cast<const double2*>(p.A0) + b * p.A0_stride * N;
         s.y[j] = a0[j];
+        double sn, cs;
+        sincos(bj * hh, &sn, &cs);
+        s.rot[j] = make_double2(cs, sn);
     }
-    for (int m = tid; m < M; m += nt) s.At[m] = make_double2(0.0, 0.0);  // empty grid slots stay 0
-    __syncthreads();
+    for (int m = tid; m < comb_seq_words(M); m += T) {
+        s.At[m] = make_double2(0.0, 0.0);  // empty grid slots and the padding stay 0
+        s.Y[m]  = make_double2(0.0, 0.0);
+    }
+    for (int m = tid; m < M + kPad; m += T) s.R[m] = make_double2(0.0, 0.0);
+    comb_sync<W>();
 
     double2* tr = p.A_trace ? reinterpret_cast<double2*>(p.A_trace) + b * p.n_saved * N : nullptr;
     if (tr) {
-        for (int j = tid; j < N; j += nt) tr[j] = s.y[j];
+        for (int j = tid; j < N; j += T) tr[j] = s.y[j];
         tr += N;
     }
-    double pm[4] = {0.0, 0.0, 0.0, 0.0};  // waves tid, tid+nt, ... (N <= 128, nt >= 32)
+    double pm[4] = {0.0, 0.0, 0.0, 0.0};  // waves tid, tid+T, ... (N <= 128, T >= 32)
     if (p.Pmax) {
         int q = 0;
-        for (int j = tid; j < N; j += nt, ++q) pm[q] = fma(s.y[j].y, s.y[j].y, s.y[j].x * s.y[j].x);
+        for (int j = tid; j < N; j += T, ++q) pm[q] = fma(s.y[j].y, s.y[j].y, s.y[j].x * s.y[j].x);
     }
-
-    const int    n_steps = p.n_steps;
-    const double z0 = p.z0, z_max = p.z_max;
-    const double step = (z_max - z0) / (double)n_steps;  // numpy.linspace arithmetic
-    double       zi = z0, di = 0.0;
-    int          save_ctr = p.save_every;
-    int32_t      bad = FPA_POINT_OK;
+    int     save_ctr = p.save_every;
+    int32_t bad = FPA_POINT_OK;
+    double2* const Yc = s.Y;  // Yc[q] = X_{M-1-q}, q in [0, 2M-2]
 
     for (int i = 0; i < n_steps; ++i) {
-        di += 1.0;
-        const double zn = (i + 1 == n_steps) ? z_max : __dadd_rn(__dmul_rn(di, step), z0);
-        const double h = zn - zi, hh = 0.5 * h, h6 = h / 6.0, h3 = h6 + h6;
-        for (int j = tid; j < N; j += nt) {
-            const double2 v = s.y[j];
-            s.ys[j] = v;
-            s.yn[j] = v;
-        }
-        __syncthreads();
+        const bool resync = (i % kCombResync) == 0;
+        const double zi = fma((double)i, h, z0);
         int nf = 0;
-        comb_stage(s, p, zi, gamma, nha, h6, hh, false, p.check && i > 0 && bad == FPA_POINT_OK, nf);
-        if (p.check && i > 0 && bad == FPA_POINT_OK) {
-            if (__syncthreads_or(nf)) bad = i - 1;  // the state produced by step i-1 was not finite
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            // ---- phases and the rotated stage state on the grid (thread j owns wave j)
+            for (int j = tid; j < N; j += T) {
+                double2 e;
+                if (stage == 0) {
+                    if (resync) {
+                        double sn, cs;
+                        sincos(s.beta[j] * zi, &sn, &cs);
+                        e = make_double2(cs, sn);
+                    } else {
+                        e = s.E[j];
+                    }
+                    const double2 v = s.y[j];
+                    s.ys[j] = v;
+                    s.yn[j] = v;
+                    if (p.check && (nonfinite(v.x) || nonfinite(v.y))) nf = 1;
+                } else if (stage == 2) {
+                    e = s.Eh[j];
+                } else {  // stage 1: z + h/2, stage 3: z + h
+                    const double2 r = s.rot[j], e0 = stage == 1 ? s.E[j] : s.Eh[j];
+                    e = make_double2(fma(-e0.y, r.y, e0.x * r.x), fma(e0.x, r.y, e0.y * r.x));
+                }
+                if (stage == 1) s.Eh[j] = e;
+                if (stage == 0 || stage == 3) s.E[j] = e;  // after stage 3: the next step's phase
+                const double2 a = s.ys[j];
+                s.At[padx(s.slot[j])] = make_double2(fma(-a.y, e.y, a.x * e.x), fma(a.x, e.y, a.y * e.x));
+                if (stage == 3) s.Eh[j] = e;               // phase this stage's conj(E) uses
+            }
+            comb_sync<W>();
+            // ---- X_d = sum_m At[m+d] conj(At[m]), d in [0, M): stored mirrored for the convolution
+            tiled_correlation<true, TILE, SPLIT, W>(s.At, s.At, M, M, tid, [&](int d, double re, double im) {
+                Yc[padx(M - 1 - d)] = make_double2(re, im);
+                Yc[padx(M - 1 + d)] = make_double2(re, -im);
+            });
+            comb_sync<W>();
+            // ---- R_n = sum_k At[k] X_{n-k} = sum_k At[k] Yc[(M-1-n) + k]; output o = M-1-n
+            tiled_correlation<false, TILE, SPLIT, W>(s.At, Yc, M, M, tid, [&](int o, double re, double im) {
+                s.R[M - 1 - o] = make_double2(re, im);
+            });
+            comb_sync<W>();
+            // ---- k_n = -(alpha/2) x + i*gamma*conj(E_n) R_n and the RK4 bookkeeping
+            const double wa = (stage == 0 || stage == 3) ? h6 : h3;
+            const double wb = stage == 2 ? h : hh;
+            for (int j = tid; j < N; j += T) {
+                const double2 r = s.R[s.slot[j]];
+                const double2 e = stage == 0 ? s.E[j] : s.Eh[j];
+                const double2 x = s.ys[j];
+                const double  fr = fma(r.y, e.y, r.x * e.x);
+                const double  fi = fma(r.y, e.x, -(r.x * e.y));
+                const double  kr = fma(nha, x.x, -(gamma * fi));
+                const double  ki = fma(nha, x.y, gamma * fr);
+                const double2 acc = s.yn[j];
+                if (stage == 3) {
+                    s.y[j] = make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y));
+                } else {
+                    const double2 y0 = s.y[j];
+                    s.yn[j] = make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y));
+                    s.ys[j] = make_double2(fma(wb, kr, y0.x), fma(wb, ki, y0.y));
+                }
+            }
+            // no barrier: the next stage's first loop touches only what this thread wrote
         }
-        comb_stage(s, p, zi + hh, gamma, nha, h3, hh, false, false, nf);
-        comb_stage(s, p, zi + hh, gamma, nha, h3, h, false, false, nf);
-        comb_stage(s, p, zi + h, gamma, nha, h6, 0.0, true, false, nf);
-        zi = zn;
-
+        if (p.check && i > 0 && bad == FPA_POINT_OK) {
+            const int any = W == 1 ? __any_sync(0xffffffffu, nf) : __syncthreads_or(nf);
+            if (any) bad = i - 1;  // the state produced by step i-1 was not finite
+        }
         if (--save_ctr == 0) {
             save_ctr = p.save_every;
             if (tr) {
-                for (int j = tid; j < N; j += nt) tr[j] = s.y[j];
+                for (int j = tid; j < N; j += T) tr[j] = s.y[j];
                 tr += N;
             }
             if (p.Pmax) {
                 int q = 0;
-                for (int j = tid; j < N; j += nt, ++q) {
+                for (int j = tid; j < N; j += T, ++q) {
                     const double P = fma(s.y[j].y, s.y[j].y, s.y[j].x * s.y[j].x);
                     pm[q] = (P != P || pm[q] != pm[q]) ? qnan() : fmax(pm[q], P);
                 }
@@ -204,18 +312,30 @@ __global__ void nwave_comb_kernel(const CombParams p) {
     }
     if (p.check && bad == FPA_POINT_OK) {
         int nf = 0;
-        for (int j = tid; j < N; j += nt) nf |= (nonfinite(s.y[j].x) || nonfinite(s.y[j].y)) ? 1 : 0;
-        if (__syncthreads_or(nf)) bad = n_steps - 1;
+        for (int j = tid; j < N; j += T) nf |= (nonfinite(s.y[j].x) || nonfinite(s.y[j].y)) ? 1 : 0;
+        const int any = W == 1 ? __any_sync(0xffffffffu, nf) : __syncthreads_or(nf);
+        if (any) bad = n_steps - 1;
     }
     if (p.status && tid == 0) p.status[b] = bad;
     if (p.A_end) {
         double2* o = reinterpret_cast<double2*>(p.A_end) + b * N;
-        for (int j = tid; j < N; j += nt) o[j] = s.y[j];
+        for (int j = tid; j < N; j += T) o[j] = s.y[j];
     }
     if (p.Pmax) {
         int q = 0;
-        for (int j = tid; j < N; j += nt, ++q) p.Pmax[b * N + j] = pm[q];
+        for (int j = tid; j < N; j += T, ++q) p.Pmax[b * N + j] = pm[q];
     }
+}
+
+template <int W>
+static cudaError_t comb_launch_w(const CombParams& p, size_t smem_point, cudaStream_t st) {
+    constexpr int PPC  = kCombThreads / (32 * W);
+    const size_t  smem = smem_point * PPC;
+    cudaError_t   e = cudaFuncSetAttribute(nwave_comb_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)((p.n_points + PPC - 1) / PPC);
+    nwave_comb_kernel<W><<<blocks, kCombThreads, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 // d->grid_slot: device pointer to the N grid slots; span = number of grid slots covered.
@@ -245,13 +365,14 @@ int nwave_comb_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     p.status       = d->status;
     p.check        = (d->flags & FPA_CHECK_NAN) ? 1 : 0;
 
-    const size_t smem = comb_smem_bytes(N, M);
-    int threads = ((2 * M - 1) + 31) / 32 * 32;  // one thread per C_s
-    if (threads > 1024) threads = 1024;
-    cudaError_t e = cudaFuncSetAttribute(nwave_comb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(nwave_comb_kernel)");
-    nwave_comb_kernel<<<(unsigned)d->n_points, threads, smem, st>>>(p);
-    e = cudaGetLastError();
+    const size_t smem_point = comb_point_doubles(N, M) * sizeof(double);
+    int          dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // one warp per point once the batch can give every SM sub-partition a point of its own (and 8 points
+    // fit into a CTA's shared memory); below that one CTA per point, for latency
+    const bool  wide = d->n_points >= 4 * (int64_t)sms && smem_point * 8 <= 200 * 1024;
+    cudaError_t e = wide ? comb_launch_w<1>(p, smem_point, st) : comb_launch_w<8>(p, smem_point, st);
     if (e != cudaSuccess) return cuda_fail(e, "nwave_comb_kernel launch");
     return FPA_OK;
 }
@@ -259,8 +380,10 @@ int nwave_comb_launch(const fpa_nwave_desc* d, cudaStream_t st) {
 }  // namespace fpa
 
 extern "C" double fpa_nwave_comb_flops_per_step(int32_t n_waves, int32_t grid_span) {
-    // per RHS: C (half the ordered pairs, complex MAC = 8 flops) 4*M^2, correlation 8*N*M, and 30*N for
-    // phases, rotation, conj(E)*R and the assembly; per step 4 RHS + 26*N for the RK4 combination.
+    // per RHS: X_d for d >= 0 over the non-zero products, M^2/2 complex MACs (8 flops) = 4*M^2; the
+    // convolution with X on the N occupied slots, 8*N*M; 30*N for phases, rotation, conj(E)*R and the
+    // assembly.  Per step 4 RHS + 26*N for the RK4 combination.  (The kernel executes the regular,
+    // zero-padded M^2 + M^2 form: the padding is not credited.)
     const double M = grid_span, N = n_waves;
     return 4.0 * (4.0 * M * M + 8.0 * N * M + 30.0 * N) + 26.0 * N;
 }

@@ -74,15 +74,17 @@ def yaman_desc(B, dbeta, consts, z_max, n_steps, save_every, flags, trace=None, 
 peak_tf, _ = fpa._device.fp64_peak(iters=2048)
 out["fp64_peak_tflops_measured"] = peak_tf
 
+fp, ds = fpa.frequency_plan, fpa.dispersion
+om = fp.plan_from_wavelengths(1550e-9, 1560e-9, 1555e-9)
+sp = fp.infer_symmetry_from_omegas(*om)
+disp = ds.dispersion_params_from_D_S(fp.lambda_from_omega(sp.omega_c), 0.02, 0.02, 0.0, D_units="ps/nm/km",
+                                     S_units="ps/nm^2/km", dSdlmbd_units="ps/nm^3/km", omega_ref=sp.omega_c)
+
+cfg = fpa.config.custom_simulation_config(z_max=1000.0, dz=0.1, save_every=10)
+kw = dict(gamma=11.5e-3, alpha=float(np.log(10) / 10 * 0.9 / 1000), omega=om, p_in=[0.5, 0.5, 1e-5, 1e-5], dispersion=disp)
+
 # ---- config 1a: one run through the reference-shaped host API
 if want("config1a"):
-    fp, ds = fpa.frequency_plan, fpa.dispersion
-    om = fp.plan_from_wavelengths(1550e-9, 1560e-9, 1555e-9)
-    sp = fp.infer_symmetry_from_omegas(*om)
-    disp = ds.dispersion_params_from_D_S(fp.lambda_from_omega(sp.omega_c), 0.02, 0.02, 0.0, D_units="ps/nm/km",
-                                         S_units="ps/nm^2/km", dSdlmbd_units="ps/nm^3/km", omega_ref=sp.omega_c)
-    cfg = fpa.config.custom_simulation_config(z_max=1000.0, dz=0.1, save_every=10)
-    kw = dict(gamma=11.5e-3, alpha=float(np.log(10) / 10 * 0.9 / 1000), omega=om, p_in=[0.5, 0.5, 1e-5, 1e-5], dispersion=disp)
     fpa.simulation.run_single_simulation(cfg, **kw)
     t0 = time.perf_counter()
     for _ in range(5):
@@ -155,7 +157,7 @@ if want("config5"):
     rng = np.random.default_rng(0)
     phases = rng.uniform(0, 2 * np.pi, 64)
     cfg5 = fpa.config.custom_simulation_config(z_max=100.0, dz=0.1, save_every=100)   # 1 000 of the 1e5 steps
-    for Bn, form in ((1, "table"), (148, "table"), (1, "comb"), (148, "comb"), (1024, "comb")):
+    for Bn, form in ((1, "table"), (148, "table"), (1, "comb"), (148, "comb"), (1024, "comb"), (9472, "comb")):
         A0n = np.empty((Bn, 64), dtype=complex)
         for b, pw in enumerate(np.linspace(0.1, 1.0, Bn)):
             p = np.full(64, 1e-12)

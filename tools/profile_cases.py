@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """tools/profile_cases.py <case> -- one small launch sequence per secondary kernel, for ncu captures.
   trace : yaman4_fast_kernel<TRACE>, 2e5 points x 2500 steps, save_every = 1 (32 GB written)
-  comb  : nwave_comb_kernel, N = 64, B = 1024, 200 steps
+  comb  : nwave_comb_kernel<1> (warp per point), N = 64, B = 4736, 200 steps
+  comb1 : nwave_comb_kernel<8> (CTA per point), N = 64, B = 1, 2000 steps
   table : nwave_rk4_kernel, N = 64, B = 148, 100 steps
 """
 import ctypes as C
@@ -44,12 +45,12 @@ else:
     plan = nw.uniform_comb_plan(w0, 2 * np.pi * 100e9, range(-32, 32))
     disp = ds.DispersionParams(omega_ref=w0, beta2=-2.57e-29, beta3=3.30e-41, beta4=-1.63e-55)
     beta = nw.beta_per_wave(plan, disp)
-    Bn, steps = (1024, 200) if case == "comb" else (148, 100)
+    Bn, steps = {"comb": (4736, 200), "comb1": (1, 2000), "table": (148, 100)}[case]
     rng = np.random.default_rng(0)
     A0 = np.sqrt(np.full((Bn, 64), 1e-6)) * np.exp(1j * rng.uniform(0, 6.28, (Bn, 64)))
     A0[:, [28, 36]] = np.sqrt(np.linspace(0.1, 1.0, Bn))[:, None]
     cfg = fpa.config.custom_simulation_config(z_max=steps * 0.1, dz=0.1, save_every=100)
     for _ in range(3):
         nw.run_nwave_simulation(cfg, plan, gamma=11.5e-3, alpha=2e-4, A0=A0, beta=beta, outputs=("end",),
-                                form="comb" if case == "comb" else "table")
+                                form="comb" if case.startswith("comb") else "table")
 print("done", case)

@@ -64,8 +64,8 @@ int main(int argc, char** argv) {
     cudaFree(0);  // primary context
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, 0);
-    const int64_t B = 1000000;
-    const int     n_steps = 2500;
+    const int64_t B = getenv("LAB_POINTS") ? atoll(getenv("LAB_POINTS")) : 1000000;
+    const int     n_steps = getenv("LAB_STEPS") ? atoi(getenv("LAB_STEPS")) : 2500;
     std::vector<double> dbeta(B);
     for (int64_t i = 0; i < B; ++i) dbeta[i] = -0.015 + 0.03 * (double)i / (double)B;
     const double consts[10] = {11.5e-3, 1.1512925464970228e-4, 0.31622776601683794, 0, 0.31622776601683794, 0,
