@@ -211,6 +211,9 @@ def run_ours(args) -> None:
     L.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     lam1, lam3 = workload_axes(rank, world, args.scaling)
@@ -368,7 +371,7 @@ def run_ours(args) -> None:
         "clocks": clocks,
         "roofline": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/r1_ncu_yaman4_sweep_kernel_sass.csv)",
+                     "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/r1_ncu_yaman4_sweep_kernel.csv)",
                      "kernel": "yaman4_sweep_kernel<LOSS,128,4> (plan + dbeta prologue, fused RK4 z-loop, gain epilogue; "
                                "every launch of the timed region, CUDA events on the launching stream)",
                      "kernel_ms": kernel_ms, "library": lib.fpa_version().decode(),
