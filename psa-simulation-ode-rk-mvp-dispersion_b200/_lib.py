@@ -221,3 +221,21 @@ def f64(a) -> np.ndarray:
 
 def c128(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """Page-locked host array (`fpa_host_alloc`).  Result buffers of this kind passed to the sweep
+    entry points (`out=` of `scan_mismtach.sweep_gain_2d`) are written by the kernel directly, with
+    no staging copy.  The memory is released when the array is garbage-collected (keep the array
+    itself alive while views of it are in use)."""
+    import weakref
+
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(v) for v in shape)
+    count = int(np.prod(shape))
+    nbytes = max(count * np.dtype(dtype).itemsize, 1)
+    p = C.c_void_p()
+    check(lib().fpa_host_alloc(C.byref(p), nbytes))
+    buf = (C.c_char * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    weakref.finalize(arr, lib().fpa_host_free, C.c_void_p(p.value))
+    return arr

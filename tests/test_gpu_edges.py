@@ -127,3 +127,26 @@ def test_long_single_run_keeps_phase_in_sync(gpu, oracle):
     z, A = oracle.march_interval(oracle.yaman_rhs_p, 200.0, 0.01, A0, oracle.YamanPoint(11.5e-3, 2e-4, 4e-4),
                                  save_every=1000)
     assert np.max(np.abs(fast[:21] - A)) / np.max(np.abs(A)) < 1e-11
+
+
+def test_sweep_results_written_into_pinned_host_buffers(gpu, golden):
+    """`fpa_yaman4_sweep_host` lets the kernel store into pinned result buffers (zero-copy); with
+    pageable buffers it stages through device memory.  Same bits either way, NaN placement included."""
+    b2, b3, b4, wref = golden["b4_beta"]
+    disp = gpu.dispersion.DispersionParams(omega_ref=wref, beta2=b2, beta3=b3, beta4=b4)
+    cfg = gpu.config.custom_simulation_config(z_max=30.0, dz=0.2, save_every=10)
+    lam1 = np.linspace(1545e-9, 1555e-9, 37)
+    lam3 = np.linspace(1400e-9, 1700e-9, 501)          # wide enough to hold invalid plans
+    kw = dict(cfg=cfg, lambda_p1_m=lam1, lambda_signal_m=lam3, lambda_p2_m=1558e-9, gamma=11.5e-3, alpha=1e-4,
+              p_in=golden["b4_p_in"], dispersion=disp, gain_unit="dB")
+    pageable = gpu.scan_mismtach.sweep_gain_2d(**kw)
+    bufs = {k: gpu._lib.pinned_empty((37, 501), dt) for k, dt in
+            (("gain_lin", np.float64), ("dbeta", np.float64), ("valid", np.int32), ("status", np.int32))}
+    for v in bufs.values():
+        v.fill(-7)
+    pinned = gpu.scan_mismtach.sweep_gain_2d(out=bufs, **kw)
+    assert pinned["gain_lin"] is bufs["gain_lin"]
+    for k in ("gain", "gain_lin", "dbeta", "valid", "status"):
+        assert np.array_equal(pinned[k], pageable[k], equal_nan=True), k
+    assert np.isfinite(pinned["gain"]).any()
+

@@ -517,6 +517,111 @@ class BlockScheduler:
         return misses, span, order, orient, times
 
 
+    # ---- partial schedules as explicit states (beam search)
+    def _initial(self):
+        return dict(order=[], orient={}, times={}, npred=list(self.npred), earliest=list(self.earliest),
+                    ready={i for i in range(self.n) if self.npred[i] == 0}, t_last=-1, t_last_fp=-2, prev=None,
+                    misses=0, mask=0, left_T=sum(self.isT))
+
+    def _expand(self, st, w):
+        """Candidates (score, j, orientation, issue time, hit, miss) of a partial schedule, best first;
+        same local score as run()."""
+        seq = self.seq
+        ready = st["ready"]
+        readyT = {k for k in ready if self.isT[k]}
+        cands = []
+        any_hit = False
+        for j in ready:
+            x = seq[j]
+            est = max(st["t_last"] + 1, st["earliest"][j])
+            if x.is_fp64:
+                est = max(est, st["t_last_fp"] + 2)
+            if est - st["t_last"] > MAX_STALL or (not st["order"] and est > 0):
+                continue
+            for o, fj in enumerate(self.of[j]):
+                hit = False
+                if x.is_fp64 and st["prev"] is not None and est <= st["t_last"] + 2:
+                    pj, po = st["prev"]
+                    pf, pd = self.of[pj][po], self.defs_r[pj]
+                    hit = any(pf.get(sl) == r and r not in pd for sl, r in fj.items())
+                cands.append((j, o, est, hit))
+                any_hit |= hit and self.isT[j]
+        scored = []
+        for j, o, est, hit in cands:
+            x = seq[j]
+            sc = 0.0
+            miss = self.isT[j] and not hit
+            if miss:
+                sc += w["miss"]
+            if self.isT[j] and hit:
+                sc -= w["thit"]
+            if x.is_fp64:
+                newly = {k for k, _ in self.succ[j] if st["npred"][k] == 1 and self.isT[k]}
+                fert = len(self.hits_after[(j, o)] & ((readyT | newly) - {j}))
+                if fert:
+                    sc -= w["fert"] + w["fert2"] * min(fert, 4)
+                else:
+                    if readyT - {j}:
+                        sc += w["nofert"]
+                    if not self.isT[j] and any(not (st["mask"] >> k) & 1 for k in self.hits_after[(j, o)]):
+                        sc += w["hold"]
+            elif any_hit:
+                sc += w["brk"]
+            sc += w["stall"] * (est - (st["t_last"] + 1)) - w["cp"] * self.cp[j]
+            scored.append((sc, j, o, est, hit, miss))
+        scored.sort(key=lambda c: c[0])
+        return scored
+
+    def _child(self, st, cand):
+        """State after issuing candidate `cand`."""
+        _sc, j, o, est, _hit, miss = cand
+        npred = list(st["npred"])
+        earliest = list(st["earliest"])
+        ready = set(st["ready"])
+        ready.discard(j)
+        for k, lat in self.succ[j]:
+            npred[k] -= 1
+            if est + lat > earliest[k]:
+                earliest[k] = est + lat
+            if npred[k] == 0:
+                ready.add(k)
+        isf = self.seq[j].is_fp64
+        ch = dict(npred=npred, earliest=earliest, ready=ready, t_last=est,
+                  t_last_fp=est if isf else st["t_last_fp"], prev=(j, o) if isf else None,
+                  misses=st["misses"] + (1 if miss else 0), mask=st["mask"] | (1 << j),
+                  left_T=st["left_T"] - (1 if self.isT[j] else 0))
+        ch["order"] = st["order"] + [j]
+        ch["orient"] = dict(st["orient"])
+        ch["orient"][j] = o
+        ch["times"] = dict(st["times"])
+        ch["times"][j] = est
+        return ch
+
+    def beam_search(self, width=24, topk=5, stall_cost=0.05, w=None):
+        """Keep the `width` best partial schedules of each length; each is extended by its `topk` best
+        candidates.  States with the same set of issued instructions and the same last instruction
+        are merged.  Rank: misses so far + stall_cost * time + an estimate for the three-register
+        instructions still to come."""
+        w = dict(DEFAULT_W if w is None else w)
+        beam = [self._initial()]
+        for _depth in range(self.n):
+            children = {}
+            for st in beam:
+                for cand in self._expand(st, w)[:topk]:
+                    _sc, j, o, est, _hit, miss = cand
+                    key = (st["mask"] | (1 << j), j, o)
+                    rank = st["misses"] + (1 if miss else 0) + stall_cost * est + \
+                        0.15 * (st["left_T"] - (1 if self.isT[j] else 0))
+                    old = children.get(key)
+                    if old is None or rank < old[0]:
+                        children[key] = (rank, st, cand)
+            if not children:
+                return None
+            best = sorted(children.values(), key=lambda c: c[0])[:width]
+            beam = [self._child(st, cand) for _rank, st, cand in best]
+        st = min(beam, key=lambda b: b["misses"] + stall_cost * b["t_last"])
+        return st["misses"], st["t_last"], st["order"], st["orient"], st["times"]
+
     # ---- fixed order: issue times, best orientations, cost
     def evaluate(self, order):
         """(misses, span, orient, times) of a dependency-respecting order; None when a gap cannot
@@ -684,7 +789,8 @@ DEFAULT_W = dict(miss=1000.0, thit=300.0, fert=100.0, fert2=5.0, nofert=20.0, br
                  cp=0.3, noise=30.0, hold=60.0)
 
 
-def schedule_block(seq, tries=60, seed=1, stall_cost=0.05, w_over=None, polish=True, anneal_iters=0):
+def schedule_block(seq, tries=60, seed=1, stall_cost=0.05, w_over=None, polish=True, anneal_iters=0,
+                   beam_width=0):
     """Best of `tries` randomised list schedules.  Returns the new instruction list (copies, with
     A/B swaps, reuse flags, yield hints and stall counts set) and statistics."""
     bs = BlockScheduler(seq)
@@ -706,6 +812,12 @@ def schedule_block(seq, tries=60, seed=1, stall_cost=0.05, w_over=None, polish=T
         key = (res[0] + stall_cost * res[1],)
         if best is None or key < best[0]:
             best = (key, res)
+    if beam_width:
+        res = bs.beam_search(width=beam_width, stall_cost=stall_cost)
+        if res is not None:
+            key = (res[0] + stall_cost * res[1],)
+            if key < best[0]:
+                best = (key, res)
     misses, span, order, orient, times = best[1]
     if polish:
         order, (misses, span, orient, times) = bs.local_search(order, stall_cost)
@@ -845,7 +957,7 @@ def patch_function(ins, mode, tries, log, stall_cost=0.05, w_over=None, kept=Non
         m0 += th
         if mode == "sched":
             try:
-                new, st = schedule_block(seq, tries=tries, stall_cost=stall_cost, w_over=w_over)
+                new, st = schedule_block(seq, tries=tries, stall_cost=stall_cost, w_over=w_over, beam_width=48)
                 verify_block(seq, new)
             except (ValueError, AssertionError) as e:  # keep ptxas' block rather than risk it
                 log(f"  block {seq[0].addr:#x}: left as is ({e!r})")
