@@ -177,7 +177,7 @@ __device__ __forceinline__ void tiled_correlation(const double2* a, const double
 template <int W>
 __global__ void __launch_bounds__(kCombThreads) nwave_comb_kernel(const CombParams p) {
     constexpr int T     = 32 * W;            // threads per scan point
-    constexpr int PPC   = kCombThreads / T;  // points per CTA
+    const int     PPC = blockDim.x / T;      // points per CTA (W = 1: 1..8 warps, chosen by the launcher)
     constexpr int TILE  = W == 1 ? 4 : 2;
     constexpr int SPLIT = W == 1 ? 2 : 8;
     extern __shared__ __align__(16) double comb_smem_raw[];
@@ -328,13 +328,17 @@ __global__ void __launch_bounds__(kCombThreads) nwave_comb_kernel(const CombPara
 }
 
 template <int W>
-static cudaError_t comb_launch_w(const CombParams& p, size_t smem_point, cudaStream_t st) {
-    constexpr int PPC  = kCombThreads / (32 * W);
-    const size_t  smem = smem_point * PPC;
-    cudaError_t   e = cudaFuncSetAttribute(nwave_comb_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static cudaError_t comb_launch_w(const CombParams& p, size_t smem_point, int sms, cudaStream_t st) {
+    // W = 1: as many points per CTA (up to 8) as still leave two CTAs for every SM, so that a
+    // mid-sized batch spreads over the whole chip instead of filling a few SMs with 8 warps each
+    int ppc = kCombThreads / (32 * W);
+    while (W == 1 && ppc > 1 && (p.n_points + ppc - 1) / ppc < 2 * (int64_t)sms) ppc >>= 1;
+    const size_t smem = smem_point * ppc;
+    cudaError_t  e = cudaFuncSetAttribute(nwave_comb_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(smem_point * (kCombThreads / (32 * W))));
     if (e != cudaSuccess) return e;
-    const unsigned blocks = (unsigned)((p.n_points + PPC - 1) / PPC);
-    nwave_comb_kernel<W><<<blocks, kCombThreads, smem, st>>>(p);
+    const unsigned blocks = (unsigned)((p.n_points + ppc - 1) / ppc);
+    nwave_comb_kernel<W><<<blocks, 32 * W * ppc, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -372,7 +376,7 @@ int nwave_comb_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     // one warp per point once the batch can give every SM sub-partition a point of its own (and 8 points
     // fit into a CTA's shared memory); below that one CTA per point, for latency
     const bool  wide = d->n_points >= 4 * (int64_t)sms && smem_point * 8 <= 200 * 1024;
-    cudaError_t e = wide ? comb_launch_w<1>(p, smem_point, st) : comb_launch_w<8>(p, smem_point, st);
+    cudaError_t e = wide ? comb_launch_w<1>(p, smem_point, sms, st) : comb_launch_w<8>(p, smem_point, sms, st);
     if (e != cudaSuccess) return cuda_fail(e, "nwave_comb_kernel launch");
     return FPA_OK;
 }
