@@ -63,17 +63,17 @@ struct CombSmem {
 
 // words of a zero-padded, bank-skewed sequence buffer (At and Y): the sums run over whole blocks of 8
 // terms per part (at most 8 parts), so indices reach 2*roundup(M, 64) + 16
-__host__ __device__ inline int comb_seq_words(int M) {
+__host__ __device__ inline int comb_seq_words(int M, int sk) {
     const int e = 2 * ((M + 63) & ~63) + 16;
-    return e + (e >> 2) + 1;
+    return e + (e >> sk) + 1;
 }
 
-__host__ __device__ inline size_t comb_point_doubles(int N, int M) {
-    const size_t d = 2 * (size_t)(6 * N + 2 * comb_seq_words(M) + (M + kPad)) + (size_t)N + (size_t)(N + 1) / 2 + 2;
+__host__ __device__ inline size_t comb_point_doubles(int N, int M, int sk) {
+    const size_t d = 2 * (size_t)(6 * N + 2 * comb_seq_words(M, sk) + (M + kPad)) + (size_t)N + (size_t)(N + 1) / 2 + 2;
     return (d + 1) & ~(size_t)1;  // keeps every point's block 16-byte aligned
 }
 
-__device__ __forceinline__ CombSmem comb_carve(double* base, int N, int M) {
+__device__ __forceinline__ CombSmem comb_carve(double* base, int N, int M, int sk) {
     CombSmem s;
     s.y    = reinterpret_cast<double2*>(base);
     s.ys   = s.y + N;
@@ -82,8 +82,8 @@ __device__ __forceinline__ CombSmem comb_carve(double* base, int N, int M) {
     s.Eh   = s.E + N;
     s.rot  = s.Eh + N;
     s.At   = s.rot + N;
-    s.Y    = s.At + comb_seq_words(M);
-    s.R    = s.Y + comb_seq_words(M);
+    s.Y    = s.At + comb_seq_words(M, sk);
+    s.R    = s.Y + comb_seq_words(M, sk);
     s.beta = reinterpret_cast<double*>(s.R + (M + kPad));
     s.slot = reinterpret_cast<int*>(s.beta + N);
     return s;
@@ -97,28 +97,31 @@ __device__ __forceinline__ void comb_sync() {
         __syncthreads();
 }
 
-// Shared-memory position of sequence element e: one spare word after every four, so that the
-// windows of eight neighbouring TILE = 4 tiles (16-byte words 4 apart) fall into distinct banks.
-__host__ __device__ __forceinline__ int padx(int e) { return e + (e >> 2); }
+// Shared-memory position of sequence element e: one spare word after every TILE = 2^SK words, so that
+// the windows of eight neighbouring tiles (16-byte words TILE apart) fall into distinct bank groups
+// (5*tau mod 8 resp. 3*tau mod 8 are permutations) and every operand of a block of terms sits at a
+// compile-time offset from the block's first word.
+template <int SK>
+__host__ __device__ __forceinline__ int padx(int e) { return e + (e >> SK); }
+__host__ __device__ constexpr int skew_of(int tile) { return tile == 4 ? 2 : 1; }
 
 // acc[t] += a[i] (x) w[wbase + i + t]  for i in [i0, i1), t in [0, TILE);  (x) = conj(a)*w when CONJ
-// else a*w.  i0 and i1 are multiples of 8 (and wbase of 4 when TILE = 4), so inside a block of K = 8
-// terms every operand sits at a fixed offset from two base addresses; all operands of a block are loaded first
+// else a*w.  i0 and i1 are multiples of 8 and wbase of TILE, so inside a block of K = 8 terms every
+// operand sits at a compile-time offset from two base addresses; all operands of a block are loaded first
 // (independent loads in flight together), then K*TILE complex MACs run from registers.  No bounds
 // tests: the sequences are zero beyond their last element.
 template <bool CONJ, int TILE>
 __device__ __forceinline__ void sliding_mac(const double2* __restrict__ a, const double2* __restrict__ w, int wbase,
                                             int i0, int i1, double (&re)[TILE], double (&im)[TILE]) {
-    constexpr int K = 8;
+    constexpr int K = 8, SK = skew_of(TILE);
     for (int i = i0; i < i1; i += K) {
-        const double2* ap = a + padx(i);
-        const double2* wp = w + padx(wbase + i);
-        const int      ph = (TILE % 4 == 0) ? 0 : ((wbase + i) & 3);  // position inside the group of four
+        const double2* ap = a + padx<SK>(i);
+        const double2* wp = w + padx<SK>(wbase + i);
         double2 av[K], wv[K + TILE - 1];
 #pragma unroll
-        for (int k = 0; k < K; ++k) av[k] = ap[k + (k >> 2)];
+        for (int k = 0; k < K; ++k) av[k] = ap[k + (k >> SK)];
 #pragma unroll
-        for (int k = 0; k < K + TILE - 1; ++k) wv[k] = wp[k + ((ph + k) >> 2)];
+        for (int k = 0; k < K + TILE - 1; ++k) wv[k] = wp[k + (k >> SK)];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
 #pragma unroll
@@ -175,17 +178,18 @@ __device__ __forceinline__ void tiled_correlation(const double2* a, const double
 }
 
 template <int W>
-__global__ void __launch_bounds__(kCombThreads) nwave_comb_kernel(const CombParams p) {
+__global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kernel(const CombParams p) {
     constexpr int T     = 32 * W;            // threads per scan point
     const int     PPC = blockDim.x / T;      // points per CTA (W = 1: 1..8 warps, chosen by the launcher)
-    constexpr int TILE  = W == 1 ? 4 : 2;
+    constexpr int TILE  = W == 1 ? 4 : 2;   // (the launcher sizes shared memory with the matching skew)
     constexpr int SPLIT = W == 1 ? 2 : 8;
+    constexpr int SK    = skew_of(TILE);
     extern __shared__ __align__(16) double comb_smem_raw[];
     const int     N = p.n_waves, M = p.span;
     const int     sub = threadIdx.x / T, tid = threadIdx.x % T;
     const int64_t b = (int64_t)blockIdx.x * PPC + sub;
     if (b >= p.n_points) return;  // W = 1: whole warps leave; W = 8: PPC = 1, never taken
-    CombSmem s = comb_carve(comb_smem_raw + (size_t)sub * comb_point_doubles(N, M), N, M);
+    CombSmem s = comb_carve(comb_smem_raw + (size_t)sub * comb_point_doubles(N, M, SK), N, M, SK);
 
     const double gamma = p.gamma[b * p.gamma_stride];
     const double nha   = -0.5 * p.alpha[b * p.alpha_stride];
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(kCombThreads) nwave_comb_kernel(const CombPara
         sincos(bj * hh, &sn, &cs);
         s.rot[j] = make_double2(cs, sn);
     }
-    for (int m = tid; m < comb_seq_words(M); m += T) {
+    for (int m = tid; m < comb_seq_words(M, SK); m += T) {
         s.At[m] = make_double2(0.0, 0.0);  // empty grid slots and the padding stay 0
         s.Y[m]  = make_double2(0.0, 0.0);
     }
@@ -254,14 +258,14 @@ __global__ void __launch_bounds__(kCombThreads) nwave_comb_kernel(const CombPara
                 if (stage == 1) s.Eh[j] = e;
                 if (stage == 0 || stage == 3) s.E[j] = e;  // after stage 3: the next step's phase
                 const double2 a = s.ys[j];
-                s.At[padx(s.slot[j])] = make_double2(fma(-a.y, e.y, a.x * e.x), fma(a.x, e.y, a.y * e.x));
+                s.At[padx<SK>(s.slot[j])] = make_double2(fma(-a.y, e.y, a.x * e.x), fma(a.x, e.y, a.y * e.x));
                 if (stage == 3) s.Eh[j] = e;               // phase this stage's conj(E) uses
             }
             comb_sync<W>();
             // ---- X_d = sum_m At[m+d] conj(At[m]), d in [0, M): stored mirrored for the convolution
             tiled_correlation<true, TILE, SPLIT, W>(s.At, s.At, M, M, tid, [&](int d, double re, double im) {
-                Yc[padx(M - 1 - d)] = make_double2(re, im);
-                Yc[padx(M - 1 + d)] = make_double2(re, -im);
+                Yc[padx<SK>(M - 1 - d)] = make_double2(re, im);
+                Yc[padx<SK>(M - 1 + d)] = make_double2(re, -im);
             });
             comb_sync<W>();
             // ---- R_n = sum_k At[k] X_{n-k} = sum_k At[k] Yc[(M-1-n) + k]; output o = M-1-n
@@ -369,14 +373,16 @@ int nwave_comb_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     p.status       = d->status;
     p.check        = (d->flags & FPA_CHECK_NAN) ? 1 : 0;
 
-    const size_t smem_point = comb_point_doubles(N, M) * sizeof(double);
+    // shared memory per point: the warp-per-point mapping uses tiles of 4 (skew 2), the CTA-per-point one tiles of 2
+    const size_t smem_w1 = comb_point_doubles(N, M, 2) * sizeof(double);
+    const size_t smem_w8 = comb_point_doubles(N, M, 1) * sizeof(double);
     int          dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // one warp per point once the batch can give every SM sub-partition a point of its own (and 8 points
     // fit into a CTA's shared memory); below that one CTA per point, for latency
-    const bool  wide = d->n_points >= 4 * (int64_t)sms && smem_point * 8 <= 200 * 1024;
-    cudaError_t e = wide ? comb_launch_w<1>(p, smem_point, sms, st) : comb_launch_w<8>(p, smem_point, sms, st);
+    const bool  wide = d->n_points >= 4 * (int64_t)sms && smem_w1 * 8 <= 200 * 1024;
+    cudaError_t e = wide ? comb_launch_w<1>(p, smem_w1, sms, st) : comb_launch_w<8>(p, smem_w8, sms, st);
     if (e != cudaSuccess) return cuda_fail(e, "nwave_comb_kernel launch");
     return FPA_OK;
 }

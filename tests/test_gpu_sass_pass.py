@@ -15,8 +15,10 @@ def _both(gpu, fn):
     if not entry.REF_LIB.exists():
         pytest.fail("build/libfpa_b200_ref.so missing: build() did not produce the reference-schedule library")
     with gpu._lib.use_library(entry.REF_LIB) as ref:
-        assert b"ptxas schedule" in ref.fpa_version()
+        # every call of the package now goes through the reference-schedule build
+        assert gpu._lib.lib() is ref and b"ptxas schedule" in gpu._lib.lib().fpa_version()
         out_ref = fn()
+    assert b"re-scheduled" in gpu._lib.lib().fpa_version()
     return out, out_ref
 
 
