@@ -198,6 +198,13 @@ typedef struct fpa_sweep_desc {
 } fpa_sweep_desc;
 
 int fpa_yaman4_sweep_host(const fpa_sweep_desc* d, int device);
+/* The same sweep on several devices of one box from ONE process (scan points are
+ * independent, no exchange): the n1 pump rows are split into contiguous ranges of ceil(n1/n_devices)
+ * rows, one kernel per device runs concurrently, every device delivers its rows into the caller's
+ * host arrays (pinned arrays are written by the kernels directly) -- the "final gather" is the
+ * result layout itself.  Results are bit-identical to the single-device call for any device count.
+ * (bench.py / sharding.py use the other arrangement, one process per GPU with an NCCL all-gather.) */
+int fpa_yaman4_sweep_multi_host(const fpa_sweep_desc* d, int n_devices, const int* devices);
 /* Same, but all pointers (plan.lambda*, plan.dbeta, plan.valid, gain_lin, ...) are DEVICE
  * pointers and the work is queued on `stream` (asynchronous): ONE kernel launch per sweep
  * (frequency plan + Delta-beta prologue, fused RK4 loop, gain epilogue).  `scratch` is device memory

@@ -152,9 +152,11 @@ def dbeta_table(plan, *, want_omega=False, device: Optional[int] = None) -> dict
 
 
 def sweep(desc, *, want_pmax=False, want_end=False, device: Optional[int] = None,
-          out: Optional[dict] = None) -> dict:
+          out: Optional[dict] = None, devices=None) -> dict:
     """Run `fpa_yaman4_sweep_host` on a SweepDesc whose plan axes / physics are filled.
-    `out` may supply preallocated (e.g. pinned) result arrays gain_lin / dbeta / valid / status."""
+    `out` may supply preallocated (e.g. pinned) result arrays gain_lin / dbeta / valid / status.
+    `devices`: CUDA ordinals to split the pump rows over from this one process
+    (`fpa_yaman4_sweep_multi_host`)."""
     n1, n3 = desc.plan.n1, desc.plan.n3
     given = out or {}
     out = {}
@@ -173,9 +175,16 @@ def sweep(desc, *, want_pmax=False, want_end=False, device: Optional[int] = None
     desc.plan.dbeta, desc.plan.valid, desc.plan.omega = ptr(out["dbeta"]), ptr(out["valid"]), None
     desc.gain_lin, desc.status = ptr(out["gain_lin"]), ptr(out["status"])
     desc.Pmax, desc.A_end = ptr(out.get("Pmax")), ptr(out.get("A_end"))
+    if n1 * n3 == 0:
+        return out
+    if devices is not None and len(devices) > 1:
+        ids = (C.c_int * len(devices))(*[int(v) for v in devices])
+        _lib.check(_lib.lib().fpa_yaman4_sweep_multi_host(C.byref(desc), len(devices), ids))
+        return out
     dev = _lib.get_device() if device is None else int(device)
-    if n1 * n3:
-        _lib.check(_lib.lib().fpa_yaman4_sweep_host(C.byref(desc), dev))
+    if devices is not None and len(devices) == 1:
+        dev = int(devices[0])
+    _lib.check(_lib.lib().fpa_yaman4_sweep_host(C.byref(desc), dev))
     return out
 
 

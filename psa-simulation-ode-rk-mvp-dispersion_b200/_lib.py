@@ -112,6 +112,7 @@ SIGNATURES = {
     "fpa_dbeta_table_dev": (C.c_int, [C.POINTER(PlanDesc), C.c_void_p]),
     "fpa_dbeta_table_host": (C.c_int, [C.POINTER(PlanDesc), C.c_int]),
     "fpa_yaman4_sweep_host": (C.c_int, [C.POINTER(SweepDesc), C.c_int]),
+    "fpa_yaman4_sweep_multi_host": (C.c_int, [C.POINTER(SweepDesc), C.c_int, C.POINTER(C.c_int)]),
     "fpa_yaman4_sweep_scratch_bytes": (C.c_int64, [C.c_int64]),
     "fpa_yaman4_sweep_dev": (C.c_int, [C.POINTER(SweepDesc), C.c_void_p, C.c_int64, C.c_void_p]),
     "fpa_linear_rk4_batch_host": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,

@@ -115,11 +115,12 @@ def sweep_gain_2d(*, cfg: SimulationConfig, lambda_p1_m, lambda_p2_m, lambda_sig
                   alpha: float, p_in, phase_in=None, dispersion: Optional[DispersionParams] = None,
                   phase_matching_cfg: Optional[PhaseMatchingConfig] = None, length_unit: str = "m",
                   gain_unit: str = "dB", want_pmax: bool = False,
-                  device: Optional[int] = None, out: Optional[dict] = None) -> dict:
+                  device: Optional[int] = None, out: Optional[dict] = None, devices=None) -> dict:
     """max-over-saved signal gain and dbeta on the grid lambda_p1[n1] x lambda_signal[n3]
     (lambda_p2 scalar or [n1]).  Returns dict(gain[n1,n3] in gain_unit, gain_lin, dbeta, valid,
     status, n_steps).  One C-ABI call: axes up, results down.  `out` may hold preallocated
-    (pinned) arrays for gain_lin / dbeta / valid / status."""
+    (pinned) arrays for gain_lin / dbeta / valid / status.  `devices=[0, 1, ...]` splits the pump
+    rows over several GPUs of the box from this one process (bit-identical results)."""
     lam3 = _signal_axis(lambda_signal_m)
     lam1 = np.atleast_1d(np.asarray(lambda_p1_m, dtype=float))
     lam2 = np.atleast_1d(np.asarray(lambda_p2_m, dtype=float))
@@ -133,9 +134,9 @@ def sweep_gain_2d(*, cfg: SimulationConfig, lambda_p1_m, lambda_p2_m, lambda_sig
         except ValueError:
             pm_cfg = None
     n1, n3 = lam1.size, lam3.size
-    nan = np.full((n1, n3), np.nan)
     if pm_cfg is None or not _run_constants_ok(cfg, gamma, alpha, dispersion, pm_cfg, length_unit):
         # every run would raise -> all NaN; dbeta is still reported when it can be computed
+        nan = np.full((n1, n3), np.nan)
         out = {"gain": nan, "gain_lin": nan.copy(), "dbeta": nan.copy(),
                "valid": np.zeros((n1, n3), np.int32), "status": np.full((n1, n3), -1, np.int32),
                "n_steps": 0}
@@ -160,7 +161,7 @@ def sweep_gain_2d(*, cfg: SimulationConfig, lambda_p1_m, lambda_p2_m, lambda_sig
     d.length_scale = s
     d.save_every = int(cfg.save_every)
     d.flags = _lib.CHECK_NAN if cfg.check_nan else 0
-    out = _device.sweep(d, want_pmax=want_pmax, device=device, out=out)
+    out = _device.sweep(d, want_pmax=want_pmax, device=device, out=out, devices=devices)
     g = out["gain_lin"]
     with np.errstate(invalid="ignore", divide="ignore"):
         out["gain"] = g if unit == "linear" else 10.0 * np.log10(g)

@@ -150,3 +150,29 @@ def test_sweep_results_written_into_pinned_host_buffers(gpu, golden):
         assert np.array_equal(pinned[k], pageable[k], equal_nan=True), k
     assert np.isfinite(pinned["gain"]).any()
 
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_multi_device_sweep_equals_single_device(gpu, golden, pinned):
+    """`fpa_yaman4_sweep_multi_host`: pump rows split over devices from one process; same bits as one
+    device for any split (ragged row counts, more devices than rows).  On a one-GPU box the device
+    list repeats device 0, which still exercises the partitioning and the per-part pointer offsets."""
+    b2, b3, b4, wref = golden["b4_beta"]
+    disp = gpu.dispersion.DispersionParams(omega_ref=wref, beta2=b2, beta3=b3, beta4=b4)
+    cfg = gpu.config.custom_simulation_config(z_max=20.0, dz=0.2, save_every=10)
+    lam1 = np.linspace(1545e-9, 1555e-9, 13)
+    lam2 = np.linspace(1557e-9, 1559e-9, 13)           # per-row second pump: lambda2 pointer must move too
+    lam3 = np.linspace(1400e-9, 1700e-9, 257)
+    kw = dict(cfg=cfg, lambda_p1_m=lam1, lambda_signal_m=lam3, lambda_p2_m=lam2, gamma=11.5e-3, alpha=1e-4,
+              p_in=golden["b4_p_in"], dispersion=disp, gain_unit="linear", want_pmax=True)
+    one = gpu.scan_mismtach.sweep_gain_2d(**kw)
+    n_dev = gpu._lib.device_count()
+    for count in (2, 5, 16):
+        devices = [k % n_dev for k in range(count)]
+        out = None
+        if pinned:
+            out = {k: gpu._lib.pinned_empty((13, 257), dt) for k, dt in
+                   (("gain_lin", np.float64), ("dbeta", np.float64), ("valid", np.int32), ("status", np.int32))}
+        many = gpu.scan_mismtach.sweep_gain_2d(devices=devices, out=out, **kw)
+        for k in ("gain", "dbeta", "valid", "status", "Pmax"):
+            assert np.array_equal(one[k], many[k], equal_nan=True), (k, count)
+

@@ -6,9 +6,10 @@ inputs and outputs, CUDA events).  Informational: bench.py carries the headline 
   config3    1-D dbeta sweep, 1e5 points x 500 steps       (+ long variant x 50 000 steps)
   trace      trace-mode write-out: 2e5 points x 2 500 steps, save_every in {10, 1}: GB/s to HBM
   config2    N = 21 dual-pump plan, single run, 10 000 steps, full trace
-  config5    N = 64 comb, B in {1, 148}, 1 000 of the 1e5 steps (rate extrapolates linearly in z)
+  config5    N = 64 comb, B in {1, 148, 1024, 9472}, 1 000 of the 1e5 steps (rate extrapolates linearly in z)
+  multi      one process driving every GPU of the box (needs > 1 device)
 
-usage: python tools/bench_extra.py [config1a config3 trace config2 config5] > profiles/rN_extra.json
+usage: python tools/bench_extra.py [config1a config3 trace config2 config5 multi] > profiles/rN_extra.json
 """
 import ctypes as C
 import json
@@ -175,5 +176,33 @@ if want("config5"):
             "point_steps_per_s": Bn * 1000 / dt,
             "tflops_credited": plan64.flops_per_step(form) * Bn * 1000 / dt / 1e12,
             "full_1e5_steps_estimate_s": dt * 100}
+
+# ---- one process, all GPUs of the box: fpa_yaman4_sweep_multi_host (weak scaling, 1e6 points per GPU)
+if want("multi") and lib.fpa_device_count() > 1:
+    import bench as Bn
+    from oracle import fwm_oracle as O
+    od = Bn.fiber_dispersion(O)
+    dm = ds.DispersionParams(omega_ref=od.omega_ref, beta2=od.b[2], beta3=od.b[3], beta4=od.b[4])
+    cfgm = fpa.config.custom_simulation_config(z_max=Bn.Z_MAX, dz=Bn.DZ, save_every=Bn.SAVE_EVERY)
+    n_dev = lib.fpa_device_count()
+    for nd in sorted({1, 2, n_dev}):
+        rows = 1000 * nd
+        l1, l3 = np.linspace(1545e-9, 1555e-9, rows), np.linspace(1540e-9, 1565e-9, 1000)
+        bufs = {k: L.pinned_empty((rows, 1000), dt) for k, dt in
+                (("gain_lin", np.float64), ("dbeta", np.float64), ("valid", np.int32), ("status", np.int32))}
+        run = lambda: fpa.scan_mismtach.sweep_gain_2d(  # noqa: E731
+            cfg=cfgm, lambda_p1_m=l1, lambda_p2_m=Bn.LAM_P2, lambda_signal_m=l3, gamma=Bn.GAMMA, alpha=Bn.ALPHA,
+            p_in=Bn.P_IN, dispersion=dm, phase_matching_cfg=fpa.phase_matching.PhaseMatchingConfig(),
+            gain_unit="linear", devices=list(range(nd)), out=bufs)
+        run()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            run()
+            ts.append(time.perf_counter() - t0)
+        out[f"one_process_{nd}_gpus"] = {"points": rows * 1000, "steps": 2500, "wall_ms": 1e3 * min(ts),
+                                         "point_steps_per_s": rows * 1000 * 2500 / min(ts),
+                                         "api": "scan_mismtach.sweep_gain_2d(devices=[...]) -> fpa_yaman4_sweep_multi_host, "
+                                                "pinned result buffers written by the kernels"}
 
 print(json.dumps(out, indent=1))
