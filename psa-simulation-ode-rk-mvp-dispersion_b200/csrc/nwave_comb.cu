@@ -27,6 +27,17 @@
 // the step is the constant h = (z_max - z0)/n_steps like the 4-wave fast kernel.
 #include "fpa_common.cuh"
 
+#include <assert.h>
+
+// compute-sanitizer is not available on the B200 pool: -DFPA_BOUNDS_CHECK turns every shared-memory
+// sequence access of this file into a checked one (device assert), tools/bounds_check.py builds that
+// variant and runs the N-wave tests on it.
+#ifdef FPA_BOUNDS_CHECK
+#define FPA_IN_RANGE(idx, n) assert((idx) >= 0 && (idx) < (n))
+#else
+#define FPA_IN_RANGE(idx, n) ((void)0)
+#endif
+
 namespace fpa {
 
 struct CombParams {
@@ -112,11 +123,13 @@ __host__ __device__ constexpr int skew_of(int tile) { return tile == 4 ? 2 : 1; 
 // tests: the sequences are zero beyond their last element.
 template <bool CONJ, int TILE>
 __device__ __forceinline__ void sliding_mac(const double2* __restrict__ a, const double2* __restrict__ w, int wbase,
-                                            int i0, int i1, double (&re)[TILE], double (&im)[TILE]) {
+                                            int i0, int i1, int words, double (&re)[TILE], double (&im)[TILE]) {
     constexpr int K = 8, SK = skew_of(TILE);
     for (int i = i0; i < i1; i += K) {
         const double2* ap = a + padx<SK>(i);
         const double2* wp = w + padx<SK>(wbase + i);
+        FPA_IN_RANGE(padx<SK>(i) + (K - 1) + ((K - 1) >> SK), words);
+        FPA_IN_RANGE(padx<SK>(wbase + i) + (K + TILE - 2) + ((K + TILE - 2) >> SK), words);
         double2 av[K], wv[K + TILE - 1];
 #pragma unroll
         for (int k = 0; k < K; ++k) av[k] = ap[k + (k >> SK)];
@@ -144,7 +157,7 @@ __device__ __forceinline__ void sliding_mac(const double2* __restrict__ a, const
 // by shuffles; the part-0 lane calls store(o, re, im).  W warps share the tiles of one point.
 template <bool CONJ, int TILE, int SPLIT, int W, typename Store>
 __device__ __forceinline__ void tiled_correlation(const double2* a, const double2* w, int M, int n_out, int tid,
-                                                  Store store) {
+                                                  int words, Store store) {
     constexpr int LP = 32 / SPLIT;
     const int lane = tid & 31, warp = tid >> 5;
     const int part = lane / LP, tl = lane % LP;
@@ -160,7 +173,7 @@ __device__ __forceinline__ void tiled_correlation(const double2* a, const double
         double     re[TILE], im[TILE];
 #pragma unroll
         for (int t = 0; t < TILE; ++t) re[t] = im[t] = 0.0;
-        if (live) sliding_mac<CONJ, TILE>(a, w, tile * TILE, i0, i1, re, im);
+        if (live) sliding_mac<CONJ, TILE>(a, w, tile * TILE, i0, i1, words, re, im);
 #pragma unroll
         for (int d = LP; d < 32; d <<= 1) {
 #pragma unroll
@@ -227,6 +240,7 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
     int     save_ctr = p.save_every;
     int32_t bad = FPA_POINT_OK;
     double2* const Yc = s.Y;  // Yc[q] = X_{M-1-q}, q in [0, 2M-2]
+    const int      words = comb_seq_words(M, SK);
 
     for (int i = 0; i < n_steps; ++i) {
         const bool resync = (i % kCombResync) == 0;
@@ -258,18 +272,22 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
                 if (stage == 1) s.Eh[j] = e;
                 if (stage == 0 || stage == 3) s.E[j] = e;  // after stage 3: the next step's phase
                 const double2 a = s.ys[j];
+                FPA_IN_RANGE(s.slot[j], M);
                 s.At[padx<SK>(s.slot[j])] = make_double2(fma(-a.y, e.y, a.x * e.x), fma(a.x, e.y, a.y * e.x));
                 if (stage == 3) s.Eh[j] = e;               // phase this stage's conj(E) uses
             }
             comb_sync<W>();
             // ---- X_d = sum_m At[m+d] conj(At[m]), d in [0, M): stored mirrored for the convolution
-            tiled_correlation<true, TILE, SPLIT, W>(s.At, s.At, M, M, tid, [&](int d, double re, double im) {
+            tiled_correlation<true, TILE, SPLIT, W>(s.At, s.At, M, M, tid, words, [&](int d, double re, double im) {
+                FPA_IN_RANGE(padx<SK>(M - 1 - d), words);
+                FPA_IN_RANGE(padx<SK>(M - 1 + d), words);
                 Yc[padx<SK>(M - 1 - d)] = make_double2(re, im);
                 Yc[padx<SK>(M - 1 + d)] = make_double2(re, -im);
             });
             comb_sync<W>();
             // ---- R_n = sum_k At[k] X_{n-k} = sum_k At[k] Yc[(M-1-n) + k]; output o = M-1-n
-            tiled_correlation<false, TILE, SPLIT, W>(s.At, Yc, M, M, tid, [&](int o, double re, double im) {
+            tiled_correlation<false, TILE, SPLIT, W>(s.At, Yc, M, M, tid, words, [&](int o, double re, double im) {
+                FPA_IN_RANGE(M - 1 - o, M + kPad);
                 s.R[M - 1 - o] = make_double2(re, im);
             });
             comb_sync<W>();

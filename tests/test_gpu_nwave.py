@@ -131,3 +131,29 @@ def test_nwave_invariants(gpu):
         r = nw.run_nwave_simulation(gpu.config.custom_simulation_config(z_max=1.0, dz=0.125, save_every=1), gap,
                                     gamma=1.0, alpha=0.0, p_in=boom, beta=bt, form=form, outputs=("end",))
         assert r["status"][0] == 0
+
+
+@pytest.mark.parametrize("lines", [[0], [0, 1], list(range(-3, 4)), list(range(-16, 17)), [0, 1, 2, 100],
+                                   list(range(-40, 41)), list(range(0, 127, 2))])
+@pytest.mark.parametrize("batch", [2, 640])          # CTA-per-point and warp-per-point mappings
+def test_comb_equals_table_on_odd_shapes(gpu, lines, batch):
+    """Grid spans that are not multiples of the kernel's tile (2, 4) or block (8) sizes, one and two
+    lines, wide gaps, spans above 64 (several rounds of tiles): the correlation form must reproduce the
+    enumerated-triplet kernel, which shares no indexing code with it."""
+    nw = gpu.nwave
+    plan = nw.uniform_comb_plan(1.2125e15, 6.28e11, lines)
+    N = plan.n_waves
+    if N > 48 and batch > 2:
+        pytest.skip("table kernel at N > 48 and 640 points: minutes")
+    disp = gpu.dispersion.DispersionParams(1.2125e15, beta2=-2.6e-29, beta3=3.3e-41, beta4=-1.6e-55)
+    beta = nw.beta_per_wave(plan, disp)
+    rng = np.random.default_rng(N + batch)
+    A0 = np.sqrt(rng.uniform(1e-5, 2e-1, (batch, N))) * np.exp(1j * rng.uniform(0, 6.28, (batch, N)))
+    cfg = gpu.config.custom_simulation_config(z_max=4.0, dz=0.1, save_every=8)
+    t = nw.run_nwave_simulation(cfg, plan, gamma=0.02, alpha=1e-4, A0=A0, beta=beta, form="table", outputs=("end", "pmax"))
+    c = nw.run_nwave_simulation(cfg, plan, gamma=0.02, alpha=1e-4, A0=A0, beta=beta, form="comb", outputs=("end", "pmax"))
+    scale = np.max(np.abs(t["A_end"]))
+    assert np.max(np.abs(t["A_end"] - c["A_end"])) < 1e-12 * scale
+    assert np.max(np.abs(t["Pmax"] - c["Pmax"])) < 1e-12 * scale ** 2
+    assert (c["status"] == -1).all()
+
