@@ -48,6 +48,7 @@ ALPHA = float(np.log(10) / 10 * 0.5 / 1000)
 P_IN = [0.1, 0.1, 1e-7, 1e-7]
 LAM_P2 = 1558e-9
 FLOPS_PER_POINT_STEP = 568.0
+RESULT_OUT = sys.stdout      # main() replaces it with a private duplicate of the original stdout
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused sweep kernel on this workload,
 # from the committed ncu capture (cannot be measured outside a profiler): 116 KB read + 0 B written --
 # the 24 MB of per-point results are still in the 126 MB L2 when the kernel ends
@@ -140,7 +141,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is pure Python/numpy and absent on the GPU box: timed arm is oracle/fwm_oracle.py "
                 "(bit-equal restatement, pinned by oracle/pin_against_reference.py), one process per host core",
-    }))
+    }), file=RESULT_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -211,9 +212,6 @@ def run_ours(args) -> None:
     L.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     lam1, lam3 = workload_axes(rank, world, args.scaling)
@@ -394,7 +392,7 @@ def run_ours(args) -> None:
                       f"{wall:.1f} s wall, oracle/fwm_oracle.py (bit-equal port of the reference's numpy RK4)",
             "parity_max_rel_err_vs_gpu": float(np.max(np.abs(gpu_gain - cpu_gain) / np.abs(cpu_gain))),
         }
-    print(json.dumps(out))
+    print(json.dumps(out), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -411,6 +409,13 @@ def main() -> None:
                     help="skip the CPU oracle leg (profiling runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries ONE JSON line.  Anything else written to file descriptor 1 -- NCCL prints its
+    # version banner there with NCCL_DEBUG >= VERSION, libraries may print -- is sent to stderr; the
+    # result line goes to a duplicate of the original stdout.
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
