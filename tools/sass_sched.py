@@ -413,20 +413,6 @@ def fix_waits(orig, new):
 
 
 # ----------------------------------------------------------------------------------- scheduler
-def can_hit(p_fields, p_defs_r, x_fields, x_swappable):
-    """Can x (possibly A/B-swapped) take an operand from the reuse cache left by p (orientation
-    fixed)?  Returns the list of x orientations (False = as is, True = swapped) that hit."""
-    outs = []
-    for sw in ((False, True) if x_swappable else (False,)):
-        f = x_fields
-        if sw:
-            f = dict(f)
-            f["A"], f["B"] = f["B"], f["A"]
-        if any(p_fields.get(s) == r and r not in p_defs_r for s, r in f.items()):
-            outs.append(sw)
-    return outs
-
-
 class BlockScheduler:
     def __init__(self, seq):
         self.seq = seq
@@ -473,88 +459,15 @@ class BlockScheduler:
                 self.hits_after[(j, o)] = s
 
     def run(self, rng, w):
-        n, seq = self.n, self.seq
-        npred = list(self.npred)
-        earliest = list(self.earliest)
-        ready = {i for i in range(n) if npred[i] == 0}
-        order, orient, times = [], {}, {}
-        done = set()
-        t_last = -1          # issue time of the last instruction
-        t_last_fp = -2       # issue time of the last FP64 instruction
-        prev = None          # (index, oriented fields) of the last instruction when it was FP64
-        misses = 0
-        while ready:
-            best, best_s = None, None
-            readyT = {k for k in ready if self.isT[k]}
-            any_hit = False
-            cands = []
-            for j in ready:
-                x = seq[j]
-                est = max(t_last + 1, earliest[j])
-                if x.is_fp64:
-                    est = max(est, t_last_fp + 2)
-                for o, fj in enumerate(self.of[j]):
-                    hit = False
-                    if x.is_fp64 and prev is not None and est <= t_last + 2:
-                        pf, pd = prev
-                        hit = any(pf.get(sl) == r and r not in pd for sl, r in fj.items())
-                    cands.append((j, o, est, hit))
-                    any_hit |= hit and self.isT[j]
-            for j, o, est, hit in cands:
-                x = seq[j]
-                miss = self.isT[j] and not hit
-                s = 0.0
-                if miss:
-                    s += w["miss"]
-                if self.isT[j] and hit:
-                    s -= w["thit"]
-                if x.is_fp64:
-                    newly = {k for k, _ in self.succ[j] if npred[k] == 1 and self.isT[k]}
-                    fert = len(self.hits_after[(j, o)] & ((readyT | newly) - {j}))
-                    if fert:
-                        s -= w["fert"] + w["fert2"] * min(fert, 4)
-                    else:
-                        if readyT - {j}:
-                            s += w["nofert"]
-                        if not self.isT[j] and self.hits_after[(j, o)] - done:
-                            s += w["hold"]   # keep an instruction that can feed a later T for then
-                else:
-                    # integer / load instructions break the reuse chain: place them where no T
-                    # instruction is waiting for a hit
-                    if any_hit:
-                        s += w["brk"]
-                gap = est - (t_last + 1)
-                if est - t_last > MAX_STALL or (not order and est > 0):
-                    s += 1e6   # stall not encodable / nothing can delay the block's first issue
-                s += w["stall"] * gap
-                s -= w["cp"] * self.cp[j]
-                s += rng.random() * w["noise"]
-                if best_s is None or s < best_s:
-                    best, best_s = (j, o, est, hit), s
-            j, o, est, hit = best
-            x = seq[j]
-            if self.isT[j] and not hit:
-                misses += 1
-            order.append(j)
-            done.add(j)
-            orient[j] = o
-            times[j] = est
-            t_last = est
-            if x.is_fp64:
-                t_last_fp = est
-                prev = (self.of[j][o], self.defs_r[j])
-            else:
-                prev = None
-            ready.discard(j)
-            for k, lat in self.succ[j]:
-                npred[k] -= 1
-                earliest[k] = max(earliest[k], est + lat)
-                if npred[k] == 0:
-                    ready.add(k)
-        assert len(order) == n
-        span = t_last
-        return misses, span, order, orient, times
-
+        """One randomised greedy list schedule: always issue the candidate with the best local score
+        (plus noise).  Returns (misses, span, order, orient, times)."""
+        st = self._initial()
+        for _ in range(self.n):
+            cands = self._expand(st, w, rng)
+            if not cands:
+                raise ValueError("no encodable candidate (stall count above the limit)")
+            st = self._child(st, cands[0])
+        return st["misses"], st["t_last"], st["order"], st["orient"], st["times"]
 
     # ---- partial schedules as explicit states (beam search)
     def _initial(self):
@@ -562,9 +475,12 @@ class BlockScheduler:
                     ready={i for i in range(self.n) if self.npred[i] == 0}, t_last=-1, t_last_fp=-2, prev=None,
                     misses=0, mask=0, left_T=sum(self.isT))
 
-    def _expand(self, st, w):
-        """Candidates (score, j, orientation, issue time, hit, miss) of a partial schedule, best first;
-        same local score as run()."""
+    def _expand(self, st, w, rng=None):
+        """Candidates (score, j, orientation, issue time, hit, miss) of a partial schedule, best first.
+        Local score: a three-register fetch costs `miss`; a hit on a three-register instruction and a
+        candidate that can feed one of the ready three-register instructions are rewarded; a non-FP64
+        instruction is kept away from a running reuse chain; stalls and (lightly) a short critical path
+        cost; rng adds noise for the randomised restarts."""
         seq = self.seq
         ready = st["ready"]
         readyT = {k for k in ready if self.isT[k]}
@@ -607,6 +523,8 @@ class BlockScheduler:
             elif any_hit:
                 sc += w["brk"]
             sc += w["stall"] * (est - (st["t_last"] + 1)) - w["cp"] * self.cp[j]
+            if rng is not None and w.get("noise"):
+                sc += rng.random() * w["noise"]
             scored.append((sc, j, o, est, hit, miss))
         scored.sort(key=lambda c: c[0])
         return scored
@@ -777,59 +695,12 @@ class BlockScheduler:
         return order, res
 
 
-    def anneal(self, order, stall_cost, iters, rng, t_start=1.5, t_end=0.05):
-        """Simulated annealing over dependency-respecting orders: move one instruction to a random
-        position between its last predecessor and first successor; cost = misses + stall_cost*span."""
-        import math
-        n = self.n
-        succ_set = [[k for k, _ in self.succ[j]] for j in range(n)]
-        pred_set = [[i for i, _ in self.pred[j]] for j in range(n)]
-        res = self.evaluate(order)
-        cur = res[0] + stall_cost * res[1]
-        best, best_order, best_res = cur, list(order), res
-        fp = [j for j in range(n) if self.seq[j].is_fp64]
-        for it in range(iters):
-            temp = t_start * (t_end / t_start) ** (it / max(1, iters - 1))
-            if rng.random() < 0.5:
-                # move one FP64 instruction anywhere between its last predecessor and first successor
-                j = fp[int(rng.random() * len(fp))]
-                pos = {q: k for k, q in enumerate(order)}
-                lo = max([pos[i] for i in pred_set[j]], default=-1) + 1
-                hi = min([pos[k] for k in succ_set[j]], default=n) - 1   # last position j may take
-                c = pos[j]
-                if hi <= lo:
-                    continue
-                q = lo + int(rng.random() * (hi - lo + 1))
-                if q == c:
-                    continue
-                trial = order[:c] + order[c + 1:]
-                trial.insert(q, j)
-            else:
-                # move a short run of consecutive instructions (a reuse chain) as a whole
-                ln = 2 + int(rng.random() * 4)
-                c = int(rng.random() * (n - ln))
-                seg = order[c:c + ln]
-                rest = order[:c] + order[c + ln:]
-                q = max(0, min(len(rest), c + int((rng.random() - 0.5) * 80)))
-                if q == c:
-                    continue
-                trial = rest[:q] + seg + rest[q:]
-            r = self.evaluate(trial)
-            if r is None:
-                continue
-            v = r[0] + stall_cost * r[1]
-            if v <= cur or rng.random() < math.exp((cur - v) / temp):
-                order, cur, res = trial, v, r
-                if v < best - 1e-12:
-                    best, best_order, best_res = v, list(trial), r
-        return best_order, best_res
 
 DEFAULT_W = dict(miss=1000.0, thit=300.0, fert=100.0, fert2=5.0, nofert=20.0, brk=400.0, stall=6.0,
                  cp=0.3, noise=30.0, hold=60.0)
 
 
-def schedule_block(seq, tries=60, seed=1, stall_cost=0.05, w_over=None, polish=True, anneal_iters=0,
-                   beam_width=0):
+def schedule_block(seq, tries=60, seed=1, stall_cost=0.05, w_over=None, polish=True, beam_width=0):
     """Best of `tries` randomised list schedules.  Returns the new instruction list (copies, with
     A/B swaps, reuse flags, yield hints and stall counts set) and statistics."""
     bs = BlockScheduler(seq)
@@ -859,9 +730,6 @@ def schedule_block(seq, tries=60, seed=1, stall_cost=0.05, w_over=None, polish=T
                 best = (key, res)
     misses, span, order, orient, times = best[1]
     if polish:
-        order, (misses, span, orient, times) = bs.local_search(order, stall_cost)
-    if anneal_iters:
-        order, (misses, span, orient, times) = bs.anneal(order, stall_cost, anneal_iters, rng)
         order, (misses, span, orient, times) = bs.local_search(order, stall_cost)
     out = []
     for j in order:
