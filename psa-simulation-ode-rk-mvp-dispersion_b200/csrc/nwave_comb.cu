@@ -20,9 +20,9 @@
 // window of w in registers (one new shared-memory word and one broadcast per TILE complex MACs --
 // the FP64 pipe is the limiter, not the LSU), and the parts are combined with warp shuffles.
 //
-// Two mappings of the same code (template parameter W = warps per scan point):
-//   W = 1  one warp per point, 8 points per CTA, __syncwarp only: throughput for large batches;
-//   W = 8  one CTA per point, sums split 8 ways: latency for single runs / small batches.
+// Two mappings of the same code (template parameters W = warps per scan point, TILE, SPLIT):
+//   W = 1  one warp per point, up to 8 points per CTA, __syncwarp only: throughput for large batches;
+//   W = 4  one CTA per point, tiles of 2, sums split 4 ways: latency for single runs / small batches.
 // exp(i*beta_n*z) advances by a constant rotation per half step (exact sincos every kResync steps),
 // the step is the constant h = (z_max - z0)/n_steps like the 4-wave fast kernel.
 #include "fpa_common.cuh"
@@ -190,18 +190,16 @@ __device__ __forceinline__ void tiled_correlation(const double2* a, const double
     }
 }
 
-template <int W>
+template <int W, int TILE, int SPLIT>
 __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kernel(const CombParams p) {
     constexpr int T     = 32 * W;            // threads per scan point
     const int     PPC = blockDim.x / T;      // points per CTA (W = 1: 1..8 warps, chosen by the launcher)
-    constexpr int TILE  = W == 1 ? 4 : 2;   // (the launcher sizes shared memory with the matching skew)
-    constexpr int SPLIT = W == 1 ? 2 : 8;
-    constexpr int SK    = skew_of(TILE);
+    constexpr int SK    = skew_of(TILE);     // (the launcher sizes shared memory with the matching skew)
     extern __shared__ __align__(16) double comb_smem_raw[];
     const int     N = p.n_waves, M = p.span;
     const int     sub = threadIdx.x / T, tid = threadIdx.x % T;
     const int64_t b = (int64_t)blockIdx.x * PPC + sub;
-    if (b >= p.n_points) return;  // W = 1: whole warps leave; W = 8: PPC = 1, never taken
+    if (b >= p.n_points) return;  // W = 1: whole warps leave; W > 1: PPC = 1, never taken
     CombSmem s = comb_carve(comb_smem_raw + (size_t)sub * comb_point_doubles(N, M, SK), N, M, SK);
 
     const double gamma = p.gamma[b * p.gamma_stride];
@@ -349,18 +347,20 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
     }
 }
 
-template <int W>
-static cudaError_t comb_launch_w(const CombParams& p, size_t smem_point, int sms, cudaStream_t st) {
+template <int W, int TILE, int SPLIT>
+static cudaError_t comb_launch_w(const CombParams& p, int sms, cudaStream_t st) {
+    const size_t smem_point = comb_point_doubles(p.n_waves, p.span, skew_of(TILE)) * sizeof(double);
     // W = 1: as many points per CTA (up to 8) as still leave two CTAs for every SM, so that a
-    // mid-sized batch spreads over the whole chip instead of filling a few SMs with 8 warps each
-    int ppc = kCombThreads / (32 * W);
+    // mid-sized batch spreads over the whole chip instead of filling a few SMs with 8 warps each;
+    // W > 1: the CTA is the point
+    int ppc = W == 1 ? kCombThreads / 32 : 1;
     while (W == 1 && ppc > 1 && (p.n_points + ppc - 1) / ppc < 2 * (int64_t)sms) ppc >>= 1;
     const size_t smem = smem_point * ppc;
-    cudaError_t  e = cudaFuncSetAttribute(nwave_comb_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(smem_point * (kCombThreads / (32 * W))));
+    cudaError_t  e = cudaFuncSetAttribute(nwave_comb_kernel<W, TILE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(smem_point * (W == 1 ? kCombThreads / 32 : 1)));
     if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)((p.n_points + ppc - 1) / ppc);
-    nwave_comb_kernel<W><<<blocks, 32 * W * ppc, smem, st>>>(p);
+    nwave_comb_kernel<W, TILE, SPLIT><<<blocks, 32 * W * ppc, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -391,16 +391,16 @@ int nwave_comb_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     p.status       = d->status;
     p.check        = (d->flags & FPA_CHECK_NAN) ? 1 : 0;
 
-    // shared memory per point: the warp-per-point mapping uses tiles of 4 (skew 2), the CTA-per-point one tiles of 2
-    const size_t smem_w1 = comb_point_doubles(N, M, 2) * sizeof(double);
-    const size_t smem_w8 = comb_point_doubles(N, M, 1) * sizeof(double);
     int          dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // one warp per point once the batch can give every SM sub-partition a point of its own (and 8 points
     // fit into a CTA's shared memory); below that one CTA per point, for latency
-    const bool  wide = d->n_points >= 4 * (int64_t)sms && smem_w1 * 8 <= 200 * 1024;
-    cudaError_t e = wide ? comb_launch_w<1>(p, smem_w1, sms, st) : comb_launch_w<8>(p, smem_w8, sms, st);
+    const size_t smem_w1 = comb_point_doubles(N, M, skew_of(4)) * sizeof(double);
+    const bool   wide = d->n_points >= 4 * (int64_t)sms && smem_w1 * 8 <= 200 * 1024;
+    // CTA per point: 4 warps, tiles of 2, sums split 4 ways -- the fastest of the seven (W, TILE, SPLIT)
+    // shapes tried for single runs (5.8 us per step at N = 64, 4.3 at N = 21; the others 5.9 .. 7.3)
+    cudaError_t e = wide ? comb_launch_w<1, 4, 2>(p, sms, st) : comb_launch_w<4, 2, 4>(p, sms, st);
     if (e != cudaSuccess) return cuda_fail(e, "nwave_comb_kernel launch");
     return FPA_OK;
 }

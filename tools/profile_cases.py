@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """tools/profile_cases.py <case> -- one small launch sequence per secondary kernel, for ncu captures.
   trace : yaman4_fast_kernel<TRACE>, 2e5 points x 2500 steps, save_every = 1 (32 GB written)
-  comb  : nwave_comb_kernel<1> (warp per point), N = 64, B = 4736, 200 steps
-  comb1 : nwave_comb_kernel<8> (CTA per point), N = 64, B = 1, 2000 steps
+  comb  : nwave_comb_kernel<1,4,2> (warp per point), N = 64, B = 4736, 200 steps
+  comb1 : nwave_comb_kernel<4,2,4> (CTA per point), N = 64, B = 1, 2000 steps
   table : nwave_rk4_kernel, N = 64, B = 148, 100 steps
 """
 import ctypes as C
