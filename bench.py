@@ -385,9 +385,10 @@ def run_ours(args) -> None:
         cores = os.cpu_count() or 1
         n_pts = max(64, 40 * cores)      # ~10 s of wall time on the box's cores
         cpu_value, wall, idx, cpu_gain = cpu_sample(n_pts, cores, seed=0)
+        one_core, _, _, _ = cpu_sample(8, 1, seed=1)          # the reference as shipped: one thread
         gpu_gain = gain_dev.reshape(-1)[idx]
         out["cpu_baseline"] = {
-            "value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+            "value": cpu_value, "unit": UNIT, "cores": cores, "value_1core": one_core, "kind": "port",
             "sample": f"{n_pts} random points (default_rng(0)) of the 1e6-point grid x {n_steps} steps, "
                       f"{wall:.1f} s wall, oracle/fwm_oracle.py (bit-equal port of the reference's numpy RK4)",
             "parity_max_rel_err_vs_gpu": float(np.max(np.abs(gpu_gain - cpu_gain) / np.abs(cpu_gain))),
