@@ -32,6 +32,22 @@
 // compute-sanitizer is not available on the B200 pool: -DFPA_BOUNDS_CHECK turns every shared-memory
 // sequence access of this file into a checked one (device assert), tools/bounds_check.py builds that
 // variant and runs the N-wave tests on it.
+// -DFPA_COMB_TIMING: thread 0 of point 0 accumulates clock64() between the phases of a stage and prints
+// the averages when the kernel ends (tools only; never in the shipped library).
+#ifdef FPA_COMB_TIMING
+#include <cstdio>
+#define FPA_TICK(k)                                   \
+    do {                                              \
+        if (b == 0 && tid == 0) {                     \
+            const long long now_ = clock64();         \
+            tk[k] += now_ - t_prev;                   \
+            t_prev = now_;                            \
+        }                                             \
+    } while (0)
+#else
+#define FPA_TICK(k) ((void)0)
+#endif
+
 #ifdef FPA_BOUNDS_CHECK
 #define FPA_IN_RANGE(idx, n) assert((idx) >= 0 && (idx) < (n))
 #else
@@ -201,6 +217,21 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
     const int64_t b = (int64_t)blockIdx.x * PPC + sub;
     if (b >= p.n_points) return;  // W = 1: whole warps leave; W > 1: PPC = 1, never taken
     CombSmem s = comb_carve(comb_smem_raw + (size_t)sub * comb_point_doubles(N, M, SK), N, M, SK);
+    // Per-wave state (y, stage state, accumulator, phases).  W == 1: a lane owns up to four waves,
+    // the state lives in shared memory.  W > 1: T >= N, a thread owns at most one wave and keeps its
+    // state in registers -- four dependent shared-memory round trips per RK4 stage less on the
+    // single-run path, whose cost is latency.
+    double2 r_y = {0, 0}, r_ys = {0, 0}, r_yn = {0, 0}, r_E = {0, 0}, r_Eh = {0, 0}, r_rot = {0, 0};
+    double  r_beta = 0.0;
+    int     r_slot = 0;
+#define WS_LD(name, j) (W == 1 ? s.name[j] : r_##name)
+#define WS_ST(name, j, v)      \
+    do {                       \
+        if (W == 1)            \
+            s.name[j] = (v);   \
+        else                   \
+            r_##name = (v);    \
+    } while (0)
 
     const double gamma = p.gamma[b * p.gamma_stride];
     const double nha   = -0.5 * p.alpha[b * p.alpha_stride];
@@ -210,13 +241,13 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
 
     for (int j = tid; j < N; j += T) {
         const double bj = p.beta[b * p.beta_stride * N + j];
-        s.beta[j] = bj;
-        s.slot[j] = p.slot[j];
+        WS_ST(beta, j, bj);
+        WS_ST(slot, j, p.slot[j]);
         const double2* a0 = reinterpret_cast<const double2*>(p.A0) + b * p.A0_stride * N;
-        s.y[j] = a0[j];
+        WS_ST(y, j, a0[j]);
         double sn, cs;
         sincos(bj * hh, &sn, &cs);
-        s.rot[j] = make_double2(cs, sn);
+        WS_ST(rot, j, make_double2(cs, sn));
     }
     for (int m = tid; m < comb_seq_words(M, SK); m += T) {
         s.At[m] = make_double2(0.0, 0.0);  // empty grid slots and the padding stay 0
@@ -227,54 +258,60 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
 
     double2* tr = p.A_trace ? reinterpret_cast<double2*>(p.A_trace) + b * p.n_saved * N : nullptr;
     if (tr) {
-        for (int j = tid; j < N; j += T) tr[j] = s.y[j];
+        for (int j = tid; j < N; j += T) tr[j] = WS_LD(y, j);
         tr += N;
     }
     double pm[4] = {0.0, 0.0, 0.0, 0.0};  // waves tid, tid+T, ... (N <= 128, T >= 32)
     if (p.Pmax) {
         int q = 0;
-        for (int j = tid; j < N; j += T, ++q) pm[q] = fma(s.y[j].y, s.y[j].y, s.y[j].x * s.y[j].x);
+        for (int j = tid; j < N; j += T, ++q) pm[q] = fma(WS_LD(y, j).y, WS_LD(y, j).y, WS_LD(y, j).x * WS_LD(y, j).x);
     }
     int     save_ctr = p.save_every;
     int32_t bad = FPA_POINT_OK;
     double2* const Yc = s.Y;  // Yc[q] = X_{M-1-q}, q in [0, 2M-2]
     const int      words = comb_seq_words(M, SK);
 
+#ifdef FPA_COMB_TIMING
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_prev = clock64();
+#endif
     for (int i = 0; i < n_steps; ++i) {
         const bool resync = (i % kCombResync) == 0;
         const double zi = fma((double)i, h, z0);
         int nf = 0;
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
+            FPA_TICK(0);  // loop overhead, save block, finite vote
             // ---- phases and the rotated stage state on the grid (thread j owns wave j)
             for (int j = tid; j < N; j += T) {
                 double2 e;
                 if (stage == 0) {
                     if (resync) {
                         double sn, cs;
-                        sincos(s.beta[j] * zi, &sn, &cs);
+                        sincos(WS_LD(beta, j) * zi, &sn, &cs);
                         e = make_double2(cs, sn);
                     } else {
-                        e = s.E[j];
+                        e = WS_LD(E, j);
                     }
-                    const double2 v = s.y[j];
-                    s.ys[j] = v;
-                    s.yn[j] = v;
+                    const double2 v = WS_LD(y, j);
+                    WS_ST(ys, j, v);
+                    WS_ST(yn, j, v);
                     if (p.check && (nonfinite(v.x) || nonfinite(v.y))) nf = 1;
                 } else if (stage == 2) {
-                    e = s.Eh[j];
+                    e = WS_LD(Eh, j);
                 } else {  // stage 1: z + h/2, stage 3: z + h
-                    const double2 r = s.rot[j], e0 = stage == 1 ? s.E[j] : s.Eh[j];
+                    const double2 r = WS_LD(rot, j), e0 = stage == 1 ? WS_LD(E, j) : WS_LD(Eh, j);
                     e = make_double2(fma(-e0.y, r.y, e0.x * r.x), fma(e0.x, r.y, e0.y * r.x));
                 }
-                if (stage == 1) s.Eh[j] = e;
-                if (stage == 0 || stage == 3) s.E[j] = e;  // after stage 3: the next step's phase
-                const double2 a = s.ys[j];
-                FPA_IN_RANGE(s.slot[j], M);
-                s.At[padx<SK>(s.slot[j])] = make_double2(fma(-a.y, e.y, a.x * e.x), fma(a.x, e.y, a.y * e.x));
-                if (stage == 3) s.Eh[j] = e;               // phase this stage's conj(E) uses
+                if (stage == 1) WS_ST(Eh, j, e);
+                if (stage == 0 || stage == 3) WS_ST(E, j, e);  // after stage 3: the next step's phase
+                const double2 a = WS_LD(ys, j);
+                FPA_IN_RANGE(WS_LD(slot, j), M);
+                s.At[padx<SK>(WS_LD(slot, j))] = make_double2(fma(-a.y, e.y, a.x * e.x), fma(a.x, e.y, a.y * e.x));
+                if (stage == 3) WS_ST(Eh, j, e);               // phase this stage's conj(E) uses
             }
+            FPA_TICK(1);  // phases + At
             comb_sync<W>();
+            FPA_TICK(2);  // barrier 1
             // ---- X_d = sum_m At[m+d] conj(At[m]), d in [0, M): stored mirrored for the convolution
             tiled_correlation<true, TILE, SPLIT, W>(s.At, s.At, M, M, tid, words, [&](int d, double re, double im) {
                 FPA_IN_RANGE(padx<SK>(M - 1 - d), words);
@@ -282,33 +319,38 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
                 Yc[padx<SK>(M - 1 - d)] = make_double2(re, im);
                 Yc[padx<SK>(M - 1 + d)] = make_double2(re, -im);
             });
+            FPA_TICK(3);  // auto-correlation
             comb_sync<W>();
+            FPA_TICK(4);  // barrier 2
             // ---- R_n = sum_k At[k] X_{n-k} = sum_k At[k] Yc[(M-1-n) + k]; output o = M-1-n
             tiled_correlation<false, TILE, SPLIT, W>(s.At, Yc, M, M, tid, words, [&](int o, double re, double im) {
                 FPA_IN_RANGE(M - 1 - o, M + kPad);
                 s.R[M - 1 - o] = make_double2(re, im);
             });
+            FPA_TICK(5);  // convolution
             comb_sync<W>();
+            FPA_TICK(6);  // barrier 3
             // ---- k_n = -(alpha/2) x + i*gamma*conj(E_n) R_n and the RK4 bookkeeping
             const double wa = (stage == 0 || stage == 3) ? h6 : h3;
             const double wb = stage == 2 ? h : hh;
             for (int j = tid; j < N; j += T) {
-                const double2 r = s.R[s.slot[j]];
-                const double2 e = stage == 0 ? s.E[j] : s.Eh[j];
-                const double2 x = s.ys[j];
+                const double2 r = s.R[WS_LD(slot, j)];
+                const double2 e = stage == 0 ? WS_LD(E, j) : WS_LD(Eh, j);
+                const double2 x = WS_LD(ys, j);
                 const double  fr = fma(r.y, e.y, r.x * e.x);
                 const double  fi = fma(r.y, e.x, -(r.x * e.y));
                 const double  kr = fma(nha, x.x, -(gamma * fi));
                 const double  ki = fma(nha, x.y, gamma * fr);
-                const double2 acc = s.yn[j];
+                const double2 acc = WS_LD(yn, j);
                 if (stage == 3) {
-                    s.y[j] = make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y));
+                    WS_ST(y, j, make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y)));
                 } else {
-                    const double2 y0 = s.y[j];
-                    s.yn[j] = make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y));
-                    s.ys[j] = make_double2(fma(wb, kr, y0.x), fma(wb, ki, y0.y));
+                    const double2 y0 = WS_LD(y, j);
+                    WS_ST(yn, j, make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y)));
+                    WS_ST(ys, j, make_double2(fma(wb, kr, y0.x), fma(wb, ki, y0.y)));
                 }
             }
+            FPA_TICK(7);  // k and the RK4 bookkeeping
             // no barrier: the next stage's first loop touches only what this thread wrote
         }
         if (p.check && i > 0 && bad == FPA_POINT_OK) {
@@ -318,13 +360,13 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
         if (--save_ctr == 0) {
             save_ctr = p.save_every;
             if (tr) {
-                for (int j = tid; j < N; j += T) tr[j] = s.y[j];
+                for (int j = tid; j < N; j += T) tr[j] = WS_LD(y, j);
                 tr += N;
             }
             if (p.Pmax) {
                 int q = 0;
                 for (int j = tid; j < N; j += T, ++q) {
-                    const double P = fma(s.y[j].y, s.y[j].y, s.y[j].x * s.y[j].x);
+                    const double P = fma(WS_LD(y, j).y, WS_LD(y, j).y, WS_LD(y, j).x * WS_LD(y, j).x);
                     pm[q] = (P != P || pm[q] != pm[q]) ? qnan() : fmax(pm[q], P);
                 }
             }
@@ -332,20 +374,31 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
     }
     if (p.check && bad == FPA_POINT_OK) {
         int nf = 0;
-        for (int j = tid; j < N; j += T) nf |= (nonfinite(s.y[j].x) || nonfinite(s.y[j].y)) ? 1 : 0;
+        for (int j = tid; j < N; j += T) nf |= (nonfinite(WS_LD(y, j).x) || nonfinite(WS_LD(y, j).y)) ? 1 : 0;
         const int any = W == 1 ? __any_sync(0xffffffffu, nf) : __syncthreads_or(nf);
         if (any) bad = n_steps - 1;
     }
+#ifdef FPA_COMB_TIMING
+    if (b == 0 && tid == 0) {
+        const double st = 4.0 * n_steps;
+        printf("comb<W=%d> cycles per stage: other %.0f | phases+At %.0f | bar %.0f | autocorr %.0f | bar %.0f | conv %.0f | "
+               "bar %.0f | k+RK4 %.0f\n", W, tk[0] / st, tk[1] / st, tk[2] / st, tk[3] / st, tk[4] / st, tk[5] / st,
+               tk[6] / st, tk[7] / st);
+    }
+#endif
     if (p.status && tid == 0) p.status[b] = bad;
     if (p.A_end) {
         double2* o = reinterpret_cast<double2*>(p.A_end) + b * N;
-        for (int j = tid; j < N; j += T) o[j] = s.y[j];
+        for (int j = tid; j < N; j += T) o[j] = WS_LD(y, j);
     }
     if (p.Pmax) {
         int q = 0;
         for (int j = tid; j < N; j += T, ++q) p.Pmax[b * N + j] = pm[q];
     }
 }
+
+#undef WS_LD
+#undef WS_ST
 
 template <int W, int TILE, int SPLIT>
 static cudaError_t comb_launch_w(const CombParams& p, int sms, cudaStream_t st) {
