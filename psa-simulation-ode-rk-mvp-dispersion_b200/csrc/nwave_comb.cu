@@ -167,19 +167,21 @@ __device__ __forceinline__ void sliding_mac(const double2* __restrict__ a, const
     }
 }
 
-// out[o] = sum_{i<M} a[i] (x) w[i + o] for o in [0, n_out): tiles of TILE outputs; the i-range is
+// out[o] = sum_{ibeg<=i<iend} a[i] (x) w[i + o] for o in [0, n_out): tiles of TILE outputs; the i-range is
 // split into SPLIT contiguous parts held by lanes LP = 32/SPLIT apart in the same warp (so the
 // eight lanes of a shared-memory wavefront work on eight neighbouring tiles of one part), combined
 // by shuffles; the part-0 lane calls store(o, re, im).  W warps share the tiles of one point.
 template <bool CONJ, int TILE, int SPLIT, int W, typename Store>
-__device__ __forceinline__ void tiled_correlation(const double2* a, const double2* w, int M, int n_out, int tid,
-                                                  int words, Store store) {
+__device__ __forceinline__ void tiled_correlation(const double2* a, const double2* w, int ibeg, int iend, int n_out,
+                                                  int tid, int words, Store store) {
+    // terms i in [ibeg, iend): ibeg is a multiple of 8 and the parts are whole blocks of 8 terms; a part
+    // that reaches past iend reads the zeros behind the sequence (callers pass iend = M for the last range)
     constexpr int LP = 32 / SPLIT;
     const int lane = tid & 31, warp = tid >> 5;
     const int part = lane / LP, tl = lane % LP;
     const int n_tiles = (n_out + TILE - 1) / TILE;
-    const int chunk   = ((M + SPLIT - 1) / SPLIT + 7) & ~7;  // whole blocks of 8 terms; the tail reads zeros
-    const int i0      = part * chunk;
+    const int chunk   = ((iend - ibeg + SPLIT - 1) / SPLIT + 7) & ~7;
+    const int i0      = ibeg + part * chunk;
     const int i1      = i0 + chunk;
     // every lane of a warp runs the same number of rounds (the shuffles below need all of them)
     const int rounds = (n_tiles + W * LP - 1) / (W * LP);
@@ -313,17 +315,29 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
             comb_sync<W>();
             FPA_TICK(2);  // barrier 1
             // ---- X_d = sum_m At[m+d] conj(At[m]), d in [0, M): stored mirrored for the convolution
-            tiled_correlation<true, TILE, SPLIT, W>(s.At, s.At, M, M, tid, words, [&](int d, double re, double im) {
+            // The sum over m stops at M-1-d: the upper half of the m-range only matters for the lower half
+            // of the d-range.  Warp per point: two passes -- m < M2 for every d (split 2 ways), then
+            // m >= M2 for d < M - M2 with all lanes (split 4 ways) -- 3 instead of 4 block-times at M = 64.
+            const int M2 = (W == 1 && M > 16) ? ((M / 2 + 15) & ~15) : M;
+            tiled_correlation<true, TILE, SPLIT, W>(s.At, s.At, 0, M2, M, tid, words, [&](int d, double re, double im) {
                 FPA_IN_RANGE(padx<SK>(M - 1 - d), words);
                 FPA_IN_RANGE(padx<SK>(M - 1 + d), words);
                 Yc[padx<SK>(M - 1 - d)] = make_double2(re, im);
                 Yc[padx<SK>(M - 1 + d)] = make_double2(re, -im);
             });
+            if (W == 1 && M2 < M) {
+                comb_sync<W>();
+                tiled_correlation<true, TILE, 4, W>(s.At, s.At, M2, M, M - M2, tid, words, [&](int d, double re, double im) {
+                    const double2 lo = Yc[padx<SK>(M - 1 - d)];
+                    Yc[padx<SK>(M - 1 - d)] = make_double2(lo.x + re, lo.y + im);
+                    if (d) Yc[padx<SK>(M - 1 + d)] = make_double2(lo.x + re, -(lo.y + im));
+                });
+            }
             FPA_TICK(3);  // auto-correlation
             comb_sync<W>();
             FPA_TICK(4);  // barrier 2
             // ---- R_n = sum_k At[k] X_{n-k} = sum_k At[k] Yc[(M-1-n) + k]; output o = M-1-n
-            tiled_correlation<false, TILE, SPLIT, W>(s.At, Yc, M, M, tid, words, [&](int o, double re, double im) {
+            tiled_correlation<false, TILE, SPLIT, W>(s.At, Yc, 0, M, M, tid, words, [&](int o, double re, double im) {
                 FPA_IN_RANGE(M - 1 - o, M + kPad);
                 s.R[M - 1 - o] = make_double2(re, im);
             });

@@ -75,7 +75,7 @@ def yaman_desc(B, dbeta, consts, z_max, n_steps, save_every, flags, trace=None, 
 peak_tf, _ = fpa._device.fp64_peak(iters=2048)
 out["fp64_peak_tflops_measured"] = peak_tf
 
-fp, ds = fpa.frequency_plan, fpa.dispersion
+fp, ds, nw = fpa.frequency_plan, fpa.dispersion, fpa.nwave
 om = fp.plan_from_wavelengths(1550e-9, 1560e-9, 1555e-9)
 sp = fp.infer_symmetry_from_omegas(*om)
 disp = ds.dispersion_params_from_D_S(fp.lambda_from_omega(sp.omega_c), 0.02, 0.02, 0.0, D_units="ps/nm/km",
@@ -133,7 +133,6 @@ if want("trace"):
 
 # ---- config 2: N = 21
 if want("config2"):
-    nw = fpa.nwave
     plan = nw.uniform_comb_plan(sp.omega_c, sp.omega_d / 5.0, range(-10, 11))
     beta = nw.beta_per_wave(plan, disp)
     p_in = np.zeros(21)
