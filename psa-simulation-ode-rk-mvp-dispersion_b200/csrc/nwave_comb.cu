@@ -140,7 +140,7 @@ __host__ __device__ constexpr int skew_of(int tile) { return tile == 4 ? 2 : 1; 
 template <bool CONJ, int TILE>
 __device__ __forceinline__ void sliding_mac(const double2* __restrict__ a, const double2* __restrict__ w, int wbase,
                                             int i0, int i1, int words, double (&re)[TILE], double (&im)[TILE]) {
-    constexpr int K = 8, SK = skew_of(TILE);
+    constexpr int K = 8, SK = skew_of(TILE);  // K = 4 or 2 and unrolling the block loop: 0 ... -12 % (measured)
     for (int i = i0; i < i1; i += K) {
         const double2* ap = a + padx<SK>(i);
         const double2* wp = w + padx<SK>(wbase + i);
