@@ -205,6 +205,16 @@ def run_ours(args) -> None:
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch N > 1 with torchrun (one rank per GPU)")
+    # The CPU leg forks worker processes: do it BEFORE this process creates a CUDA context (a forked
+    # child of a CUDA process is fragile even when it never touches the GPU).  The sample is compared
+    # with the GPU results further down.
+    cpu_leg = None
+    if world == 1 and not args.no_cpu_baseline and args.scaling == "weak":
+        cores = os.cpu_count() or 1
+        n_pts = max(64, 40 * cores)      # ~10 s of wall time on the box's cores
+        cpu_value, wall, idx, cpu_gain = cpu_sample(n_pts, cores, seed=0)
+        one_core, _, _, _ = cpu_sample(8, 1, seed=1)          # the reference as shipped: one thread
+        cpu_leg = (cores, n_pts, cpu_value, wall, idx, cpu_gain, one_core)
     if not torch.cuda.is_available() or lib.fpa_device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -381,11 +391,8 @@ def run_ours(args) -> None:
                      "hbm_note": "reduce-mode sweep: ~56 B per point per launch, HBM is idle"},
         "device": name.value.decode(),
     }
-    if world == 1 and not args.no_cpu_baseline and args.scaling == "weak":
-        cores = os.cpu_count() or 1
-        n_pts = max(64, 40 * cores)      # ~10 s of wall time on the box's cores
-        cpu_value, wall, idx, cpu_gain = cpu_sample(n_pts, cores, seed=0)
-        one_core, _, _, _ = cpu_sample(8, 1, seed=1)          # the reference as shipped: one thread
+    if cpu_leg is not None:
+        cores, n_pts, cpu_value, wall, idx, cpu_gain, one_core = cpu_leg
         gpu_gain = gain_dev.reshape(-1)[idx]
         out["cpu_baseline"] = {
             "value": cpu_value, "unit": UNIT, "cores": cores, "value_1core": one_core, "kind": "port",
