@@ -17,8 +17,9 @@
 // Same ODE as nwave.cu integrates from the enumerated triplet table (tests compare both with the
 // oracle).  Both sums have the shape  out[o] = sum_i a[i] * w[i + o]:  a thread owns a TILE of
 // adjacent outputs and a contiguous part of the i-range, keeps the TILE accumulators and a sliding
-// window of w in registers (one new shared-memory word and one broadcast per TILE complex MACs --
-// the FP64 pipe is the limiter, not the LSU), and the parts are combined with warp shuffles.
+// window of w in registers (one new shared-memory word and one broadcast per TILE complex MACs, which
+// takes the LSU out of the way: 78 % of its wavefront rate at 63 % FP64-pipe activity), and the parts
+// are combined with warp shuffles.
 //
 // Two mappings of the same code (template parameters W = warps per scan point, TILE, SPLIT):
 //   W = 1  one warp per point, up to 8 points per CTA, __syncwarp only: throughput for large batches;
