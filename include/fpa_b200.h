@@ -177,7 +177,9 @@ int fpa_dbeta_table_host(const fpa_plan_desc* d, int device);
  * `plan` holds the dispersion as the caller gave it (per length_unit) and yields the
  * reported dbeta; the integration uses dbeta/scale, gamma/scale, alpha/scale,
  * z_max*scale, dz*scale with scale = 1 (m) or 1000 (km).
- * Host pointers: only the wavelength axes go up, only gain/dbeta/status come back.
+ * Host pointers: only the wavelength axes go up, only gain/dbeta/status come back.  Result arrays in
+ * page-locked memory (fpa_host_alloc, cudaHostAlloc, cudaHostRegister) are written by the kernel itself
+ * while it runs; pageable arrays are filled by a copy after the kernel.
  *   gain_lin[b] = Pmax_signal / p_in[2]  (NaN for invalid / non-finite / <= 0 points)
  */
 typedef struct fpa_sweep_desc {
