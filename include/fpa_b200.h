@@ -114,7 +114,17 @@ typedef struct fpa_yaman4_desc {
     int32_t*      status;        /* [B] (always written when non-NULL)                    */
     double        gamma_uniform; /* with FPA_UNIFORM_PHYSICS: the value *gamma points to   */
     double        alpha_uniform; /* with FPA_UNIFORM_PHYSICS: the value *alpha points to   */
+    void*         scratch;       /* _dev entry: device memory of fpa_yaman4_scratch_bytes(B)
+                                    bytes for the z-segment scheduler, or NULL (whole-run
+                                    kernel).  Ignored by the host entry (library workspace). */
+    int64_t       scratch_bytes;
 } fpa_yaman4_desc;
+
+/* Device scratch that lets a batch of one wave of the resident warps or more run through the
+ * z-segment scheduler (persistent kernel, work items = (32 points, 64/128 RK4 steps); results are
+ * bit-identical to the whole-run kernel, the tail of the last wave shrinks from one fiber to one
+ * segment).  One size serves fpa_yaman4_rk4_batch_dev and fpa_yaman4_sweep_dev. */
+int64_t fpa_yaman4_scratch_bytes(int64_t n_points);
 
 /* n_saved for (n_steps, save_every): n_steps/save_every + 1 (integrators.py:115). */
 int64_t fpa_n_saved(int64_t n_steps, int64_t save_every);
@@ -126,6 +136,12 @@ int64_t fpa_interval_steps(double z_max, double dz);
 int fpa_yaman4_rk4_batch_dev(const fpa_yaman4_desc* d, void* stream);
 /* Host-pointer variant: H2D, one launch, D2H, synchronise.  `device` = CUDA ordinal. */
 int fpa_yaman4_rk4_batch_host(const fpa_yaman4_desc* d, int device);
+/* The same batch split over several devices of one box from ONE process (the Delta-beta sweep loop
+ * scan_mismtach.py:126-170 and any other batch of independent points): contiguous point
+ * ranges whose sizes differ by at most one, one kernel per device in flight at once, every device
+ * writes its own shard of the caller's host arrays (trace mode included: no collective).  Results are
+ * bit-identical to the single-device call for any device list. */
+int fpa_yaman4_rk4_batch_multi_host(const fpa_yaman4_desc* d, int n_devices, const int* devices);
 
 /* RHS only: dA[b,:] = rhs_yaman_simplified(z[b], A[b,:]) for B (z, A) pairs.
  * Replaces the direct Python call yaman_model.py:10-52.  Host pointers. */
@@ -191,27 +207,34 @@ typedef struct fpa_sweep_desc {
     double        z_max, dz;     /* per length unit                                       */
     double        length_scale;  /* 1.0 or 1000.0                                         */
     int64_t       save_every;
-    uint32_t      flags;         /* FPA_CHECK_NAN | FPA_PHASE_EXACT                       */
+    uint32_t      flags;         /* FPA_CHECK_NAN (FPA_PHASE_EXACT: FPA_ERR_UNSUPPORTED)  */
     uint32_t      reserved;
     double*       gain_lin;      /* [n1*n3]                                               */
     double*       Pmax;          /* [n1*n3,4] or NULL                                     */
     double*       A_end;         /* [n1*n3,4] complex128 or NULL                          */
     int32_t*      status;        /* [n1*n3] or NULL                                       */
+    int64_t       first_point;   /* sub-range of the flattened grid b = i1*n3 + i3 to run: */
+    int64_t       n_sub_points;  /*   [first_point, first_point + n_sub_points); 0, 0 = all.
+                                    Every output array is then indexed by b - first_point
+                                    (pass base + first_point to fill one full-size array).  */
 } fpa_sweep_desc;
 
 int fpa_yaman4_sweep_host(const fpa_sweep_desc* d, int device);
 /* The same sweep on several devices of one box from ONE process (scan points are
- * independent, no exchange): the n1 pump rows are split into contiguous ranges of ceil(n1/n_devices)
- * rows, one kernel per device runs concurrently, every device delivers its rows into the caller's
- * host arrays (pinned arrays are written by the kernels directly) -- the "final gather" is the
- * result layout itself.  Results are bit-identical to the single-device call for any device count.
+ * independent, no exchange): the flattened n1*n3 points are split into contiguous ranges whose sizes
+ * differ by at most one (a 1-D sweep with n1 = 1 uses every device too), one kernel per device runs
+ * concurrently, every device delivers its range into the caller's host arrays (pinned arrays are
+ * written by the kernels directly) -- the "final gather" is the result layout itself.  Results are
+ * bit-identical to the single-device call for any device count.
  * (bench.py / sharding.py use the other arrangement, one process per GPU with an NCCL all-gather.) */
 int fpa_yaman4_sweep_multi_host(const fpa_sweep_desc* d, int n_devices, const int* devices);
 /* Same, but all pointers (plan.lambda*, plan.dbeta, plan.valid, gain_lin, ...) are DEVICE
  * pointers and the work is queued on `stream` (asynchronous): ONE kernel launch per sweep
  * (frequency plan + Delta-beta prologue, fused RK4 loop, gain epilogue).  `scratch` is device memory
- * of at least fpa_yaman4_sweep_scratch_bytes(n1*n3) bytes (currently 0: it may be NULL).
- * FPA_PHASE_EXACT is not available for sweeps (use fpa_dbeta_table_* + fpa_yaman4_rk4_batch_*). */
+ * of at least fpa_yaman4_sweep_scratch_bytes(n1*n3) bytes (= fpa_yaman4_scratch_bytes) for the
+ * z-segment scheduler; with NULL the sweep runs as the whole-run kernel (same results, longer tail
+ * for batches of a few waves).  FPA_PHASE_EXACT is refused with FPA_ERR_UNSUPPORTED (use
+ * fpa_dbeta_table_* + fpa_yaman4_rk4_batch_*, which honours it). */
 int64_t fpa_yaman4_sweep_scratch_bytes(int64_t n_points);
 int fpa_yaman4_sweep_dev(const fpa_sweep_desc* d, void* scratch, int64_t scratch_bytes, void* stream);
 
@@ -288,6 +311,11 @@ double fpa_yaman4_flops_per_step(void);
 /* Pinned host memory for the e2e path. */
 int fpa_host_alloc(void** ptr, int64_t bytes);
 int fpa_host_free(void* ptr);
+/* Page-lock memory the caller already owns (e.g. a POSIX shared-memory segment several processes
+ * map: every rank registers it and its kernels store their shard of the result straight into the
+ * one host array).  Registered memory counts as pinned for every *_host entry point. */
+int fpa_host_register(void* ptr, int64_t bytes);
+int fpa_host_unregister(void* ptr);
 
 #ifdef __cplusplus
 }

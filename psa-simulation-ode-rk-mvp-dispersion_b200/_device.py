@@ -40,10 +40,24 @@ def _per_point(a, B: int, width: int, name: str, conv=f64):
     raise ValueError(f"{name} must broadcast to {B} points x {width}, got shape {arr.shape}")
 
 
+def result_array(shape, dtype, pinned: bool = True) -> np.ndarray:
+    """Result buffer handed back to the caller.  By default it comes from the library's page-locked
+    pool (`_lib.pinned_empty`): the kernels store into it directly, so the reference-named calls
+    (which never pass `out=`) get the same zero-copy delivery as a caller with its own pinned
+    buffers.  Falls back to pageable memory when page-locking fails (e.g. the locked-memory limit)."""
+    if pinned and int(np.prod(shape)) > 0:
+        try:
+            return _lib.pinned_empty(shape, dtype)
+        except _lib.FpaError:
+            pass
+    return np.empty(shape, dtype=dtype)
+
+
 def yaman4_batch(dbeta, gamma, alpha, A0, *, z0=0.0, z_max, n_steps, save_every=1, z_grid=None,
                  trace=False, end=True, pmax=False, check_nan=True, phase_exact=False,
-                 device: Optional[int] = None) -> dict:
-    """B scan points through `fpa_yaman4_rk4_batch_host`.  Returns a dict with the requested
+                 device: Optional[int] = None, devices=None) -> dict:
+    """B scan points through `fpa_yaman4_rk4_batch_host` (`devices=[...]`: split over several GPUs
+    of the box by `fpa_yaman4_rk4_batch_multi_host`, bit-identical).  Returns a dict with the requested
     outputs: A_trace [B,n_saved,4] c128, A_end [B,4] c128, Pmax [B,4] f64, status [B] i32."""
     dbeta = f64(dbeta).reshape(-1)
     B = dbeta.size
@@ -61,13 +75,14 @@ def yaman4_batch(dbeta, gamma, alpha, A0, *, z0=0.0, z_max, n_steps, save_every=
         grid = f64(z_grid).reshape(-1)
         if grid.size != n_steps + 1:
             raise ValueError("z_grid must hold n_steps+1 values")
-    out = {"status": np.empty(B, dtype=np.int32)}
+    big = B >= 4096            # single runs and small batches: not worth page-locking
+    out = {"status": result_array(B, np.int32, big)}
     if trace:
-        out["A_trace"] = np.empty((B, ns, 4), dtype=np.complex128)
+        out["A_trace"] = result_array((B, ns, 4), np.complex128, big and B * ns * 64 <= (1 << 30))
     if end:
-        out["A_end"] = np.empty((B, 4), dtype=np.complex128)
+        out["A_end"] = result_array((B, 4), np.complex128, big)
     if pmax:
-        out["Pmax"] = np.empty((B, 4), dtype=np.float64)
+        out["Pmax"] = result_array((B, 4), np.float64, big)
     d = _lib.Yaman4Desc()
     d.n_points = B
     d.dbeta = ptr(dbeta)
@@ -82,7 +97,13 @@ def yaman4_batch(dbeta, gamma, alpha, A0, *, z0=0.0, z_max, n_steps, save_every=
     d.A_end = ptr(out.get("A_end"))
     d.Pmax = ptr(out.get("Pmax"))
     d.status = ptr(out["status"])
+    if devices is not None and len(devices) > 1:
+        ids = (C.c_int * len(devices))(*[int(v) for v in devices])
+        _lib.check(_lib.lib().fpa_yaman4_rk4_batch_multi_host(C.byref(d), len(devices), ids))
+        return out
     dev = _lib.get_device() if device is None else int(device)
+    if devices is not None and len(devices) == 1:
+        dev = int(devices[0])
     _lib.check(_lib.lib().fpa_yaman4_rk4_batch_host(C.byref(d), dev))
     return out
 
@@ -154,8 +175,10 @@ def dbeta_table(plan, *, want_omega=False, device: Optional[int] = None) -> dict
 def sweep(desc, *, want_pmax=False, want_end=False, device: Optional[int] = None,
           out: Optional[dict] = None, devices=None) -> dict:
     """Run `fpa_yaman4_sweep_host` on a SweepDesc whose plan axes / physics are filled.
-    `out` may supply preallocated (e.g. pinned) result arrays gain_lin / dbeta / valid / status.
-    `devices`: CUDA ordinals to split the pump rows over from this one process
+    `out` may supply preallocated result arrays gain_lin / dbeta / valid / status; without it they
+    come from the library's page-locked pool (`result_array`), so either way the kernel delivers
+    its results straight into host memory.
+    `devices`: CUDA ordinals to split the flattened grid over from this one process
     (`fpa_yaman4_sweep_multi_host`)."""
     n1, n3 = desc.plan.n1, desc.plan.n3
     given = out or {}
@@ -164,7 +187,7 @@ def sweep(desc, *, want_pmax=False, want_end=False, device: Optional[int] = None
                        ("status", np.int32)):
         arr = given.get(key)
         if arr is None:
-            arr = np.empty((n1, n3), dtype=dtype)
+            arr = result_array((n1, n3), dtype, n1 * n3 >= 4096)
         elif arr.shape != (n1, n3) or arr.dtype != dtype or not arr.flags["C_CONTIGUOUS"]:
             raise ValueError(f"out[{key!r}] must be a C-contiguous {np.dtype(dtype)} array of shape {(n1, n3)}")
         out[key] = arr

@@ -40,6 +40,7 @@ class Yaman4Desc(C.Structure):
         ("A_trace", C.c_void_p), ("A_end", C.c_void_p), ("Pmax", C.c_void_p),
         ("status", C.c_void_p),
         ("gamma_uniform", C.c_double), ("alpha_uniform", C.c_double),
+        ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64),
     ]
 
 
@@ -69,6 +70,7 @@ class SweepDesc(C.Structure):
         ("flags", C.c_uint32), ("reserved", C.c_uint32),
         ("gain_lin", C.c_void_p), ("Pmax", C.c_void_p), ("A_end", C.c_void_p),
         ("status", C.c_void_p),
+        ("first_point", C.c_int64), ("n_sub_points", C.c_int64),
     ]
 
 
@@ -108,6 +110,8 @@ SIGNATURES = {
     "fpa_interval_steps": (C.c_int64, [C.c_double, C.c_double]),
     "fpa_yaman4_rk4_batch_dev": (C.c_int, [C.POINTER(Yaman4Desc), C.c_void_p]),
     "fpa_yaman4_rk4_batch_host": (C.c_int, [C.POINTER(Yaman4Desc), C.c_int]),
+    "fpa_yaman4_rk4_batch_multi_host": (C.c_int, [C.POINTER(Yaman4Desc), C.c_int, C.POINTER(C.c_int)]),
+    "fpa_yaman4_scratch_bytes": (C.c_int64, [C.c_int64]),
     "fpa_yaman4_rhs_host": (C.c_int, [C.c_int64] + [C.c_void_p] * 6 + [C.c_int]),
     "fpa_dbeta_table_dev": (C.c_int, [C.POINTER(PlanDesc), C.c_void_p]),
     "fpa_dbeta_table_host": (C.c_int, [C.POINTER(PlanDesc), C.c_int]),
@@ -127,6 +131,8 @@ SIGNATURES = {
     "fpa_yaman4_flops_per_step": (C.c_double, []),
     "fpa_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "fpa_host_free": (C.c_int, [C.c_void_p]),
+    "fpa_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
+    "fpa_host_unregister": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None
@@ -224,19 +230,54 @@ def c128(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.complex128)
 
 
+# Page-locked result pool.  cudaHostAlloc costs ~0.3 ms per MB, far more than a sweep launch, so blocks
+# are recycled: when the array handed to the caller is garbage-collected its block goes back to the
+# free list (up to _POOL_CAP bytes are kept; the rest is released with fpa_host_free).
+_POOL_CAP = 1 << 30
+_pool_free: dict[int, list[int]] = {}      # block size -> addresses
+_pool_bytes = 0
+
+
+def _pool_release(addr: int, size: int) -> None:
+    global _pool_bytes
+    if _lib is None:
+        return
+    if _pool_bytes + size <= _POOL_CAP:
+        _pool_free.setdefault(size, []).append(addr)
+        _pool_bytes += size
+    else:
+        _lib.fpa_host_free(C.c_void_p(addr))
+
+
 def pinned_empty(shape, dtype) -> np.ndarray:
-    """Page-locked host array (`fpa_host_alloc`).  Result buffers of this kind passed to the sweep
-    entry points (`out=` of `scan_mismtach.sweep_gain_2d`) are written by the kernel directly, with
-    no staging copy.  The memory is released when the array is garbage-collected (keep the array
-    itself alive while views of it are in use)."""
+    """Page-locked host array (`fpa_host_alloc`) from the recycling pool.  Result buffers of this kind
+    are written by the kernels directly, with no staging copy.  The block returns to the pool when
+    the array (and every view of it) is garbage-collected."""
     import weakref
 
+    global _pool_bytes
     shape = (int(shape),) if np.isscalar(shape) else tuple(int(v) for v in shape)
     count = int(np.prod(shape))
     nbytes = max(count * np.dtype(dtype).itemsize, 1)
-    p = C.c_void_p()
-    check(lib().fpa_host_alloc(C.byref(p), nbytes))
-    buf = (C.c_char * nbytes).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
-    weakref.finalize(arr, lib().fpa_host_free, C.c_void_p(p.value))
-    return arr
+    size = 1 << max(12, (nbytes - 1).bit_length())          # power-of-two size classes, >= one page
+    free = _pool_free.get(size)
+    if free:
+        addr = free.pop()
+        _pool_bytes -= size
+    else:
+        p = C.c_void_p()
+        check(lib().fpa_host_alloc(C.byref(p), size))
+        addr = p.value
+    buf = (C.c_char * size).from_address(addr)
+    weakref.finalize(buf, _pool_release, addr, size)         # buf lives as long as any view of it
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+def register_host(arr: np.ndarray) -> None:
+    """Page-lock memory the caller owns (`fpa_host_register`), e.g. a shared-memory segment that several
+    ranks map: each rank's kernels then store their shard straight into the one host array."""
+    check(lib().fpa_host_register(arr.ctypes.data, arr.nbytes))
+
+
+def unregister_host(arr: np.ndarray) -> None:
+    check(lib().fpa_host_unregister(arr.ctypes.data))

@@ -20,7 +20,8 @@ int yaman4_launch(const fpa_yaman4_desc* d, cudaStream_t st);
 int yaman4_rhs_launch(int64_t B, const double* z, const double* A, const double* gamma,
                       const double* alpha, const double* dbeta, double* dA, cudaStream_t st);
 int plan_launch(const fpa_plan_desc* d, double* dbeta_masked, cudaStream_t st);
-int yaman4_sweep_launch(const fpa_sweep_desc* d, cudaStream_t st);
+int yaman4_sweep_launch(const fpa_sweep_desc* d, void* scratch, int64_t scratch_bytes, cudaStream_t st);
+int64_t yaman4_scratch_bytes(int64_t n_points);
 int linear_launch(int64_t B, int dim, const double* y0, const double* lam, double z0, double z_max,
                   int64_t n_steps, int64_t save_every, const double* z_grid, uint32_t flags,
                   double* y_trace, double* y_end, int32_t* bad_scratch, int32_t* status,
@@ -174,10 +175,48 @@ static int nwave_dispatch(const fpa_nwave_desc* d, cudaStream_t st) {
 }
 
 // ----------------------------------------------------------------- sweep (device pointers)
-// FPA_PHASE_EXACT sweeps (the reference's arithmetic structure) run as table kernel + exact
-// integrator + the fused kernel's metric rules on the host side of the ABI; the default is the
-// single fused kernel.
-static int sweep_dev(const fpa_sweep_desc* d, cudaStream_t st) { return yaman4_sweep_launch(d, st); }
+// One fused kernel per sweep.  FPA_PHASE_EXACT is refused (FPA_ERR_UNSUPPORTED): the reference's
+// arithmetic structure is available through fpa_dbeta_table_* + fpa_yaman4_rk4_batch_*.
+static int sweep_dev(const fpa_sweep_desc* d, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
+    return yaman4_sweep_launch(d, scratch, scratch_bytes, st);
+}
+
+// Contiguous share of n items for part k of `parts`: sizes differ by at most one.
+static void balanced_range(int64_t n, int parts, int k, int64_t* lo, int64_t* hi) {
+    const int64_t base = n / parts, extra = n % parts;
+    *lo = (int64_t)k * base + (k < extra ? k : extra);
+    *hi = *lo + base + (k < extra ? 1 : 0);
+}
+
+// Drive several devices from one host thread: every part's kernel is put in flight first (a copy into
+// pageable memory blocks the host until the kernel is done), then the result copies are queued, then
+// every stream is synchronised -- also after an error on a later device.  A device that is listed twice
+// shares one workspace and stream, so the earlier part's copies are queued before its next kernel may
+// overwrite the staging buffers.
+template <typename Pending, typename Launch, typename Collect>
+static int run_on_devices(int n_devices, const int* devices, Pending* pend, Launch launch, Collect collect) {
+    bool collected[64] = {};
+    int  used = 0, rc = FPA_OK;
+    for (int k = 0; k < n_devices && rc == FPA_OK; ++k) {
+        used = k + 1;
+        for (int j = 0; j < k && rc == FPA_OK; ++j) {
+            if (devices[j] == devices[k] && pend[j].st && !collected[j]) {
+                rc = collect(pend[j], devices[j]);
+                collected[j] = true;
+            }
+        }
+        if (rc == FPA_OK) rc = launch(k, &pend[k]);
+    }
+    for (int k = 0; k < used && rc == FPA_OK; ++k)
+        if (!collected[k]) rc = collect(pend[k], devices[k]);
+    for (int k = 0; k < used; ++k) {
+        if (!pend[k].st) continue;
+        if (cudaSetDevice(devices[k]) != cudaSuccess || cudaStreamSynchronize(pend[k].st) != cudaSuccess) {
+            if (rc == FPA_OK) rc = cuda_fail(cudaGetLastError(), "multi-device call: stream synchronize");
+        }
+    }
+    return rc;
+}
 
 }  // namespace fpa
 
@@ -247,7 +286,18 @@ int fpa_yaman4_rk4_batch_dev(const fpa_yaman4_desc* d, void* stream) {
     return yaman4_launch(d, static_cast<cudaStream_t>(stream));
 }
 
-int fpa_yaman4_rk4_batch_host(const fpa_yaman4_desc* d, int device) {
+// One batch with host pointers in two steps (see the sweep below for why): batch_host_launch queues the
+// uploads and the kernel, batch_host_collect queues the result copies; the caller synchronises.
+struct PendingBatch {
+    cudaStream_t st = nullptr;
+    size_t       B = 0, n_tr = 0;
+    // device staging buffers, NULL where the kernel wrote straight into the caller's pinned array
+    double * tr = nullptr, *Ae = nullptr, *Pm = nullptr;
+    int32_t* stt = nullptr;
+    fpa_yaman4_desc user;
+};
+
+static int batch_host_check(const fpa_yaman4_desc* d) {
     FPA_REQUIRE(d != nullptr, "descriptor is NULL");
     FPA_REQUIRE(d->n_points >= 0, "n_points must be >= 0");
     FPA_REQUIRE(d->n_steps >= 1, "n_steps must be >= 1");
@@ -255,7 +305,16 @@ int fpa_yaman4_rk4_batch_host(const fpa_yaman4_desc* d, int device) {
     FPA_REQUIRE(d->dbeta && d->gamma && d->alpha && d->A0, "dbeta/gamma/alpha/A0 must be set");
     FPA_REQUIRE((d->gamma_stride | 1) == 1 && (d->alpha_stride | 1) == 1 && (d->A0_stride | 1) == 1,
                 "strides must be 0 (broadcast) or 1 (per point)");
+    FPA_REQUIRE(!(d->flags & FPA_OUT_TRACE) || d->A_trace, "FPA_OUT_TRACE needs A_trace");
+    FPA_REQUIRE(!(d->flags & FPA_OUT_PMAX) || d->Pmax, "FPA_OUT_PMAX needs Pmax");
+    FPA_REQUIRE(!(d->flags & FPA_OUT_END) || d->A_end, "FPA_OUT_END needs A_end");
+    return FPA_OK;
+}
+
+static int batch_host_launch(const fpa_yaman4_desc* d, int device, PendingBatch* pb) {
+    FPA_TRY(batch_host_check(d));
     FPA_TRY(use_device(device));
+    *pb = PendingBatch();
     const size_t B = (size_t)d->n_points;
     if (B == 0) return FPA_OK;
     const size_t ns     = (size_t)fpa_n_saved(d->n_steps, d->save_every);
@@ -264,11 +323,17 @@ int fpa_yaman4_rk4_batch_host(const fpa_yaman4_desc* d, int device) {
     const size_t n_grid = d->z_grid ? (size_t)d->n_steps + 1 : 0;
     const bool   trace = (d->flags & FPA_OUT_TRACE) != 0, endo = (d->flags & FPA_OUT_END) != 0;
     const bool   pmax = (d->flags & FPA_OUT_PMAX) != 0;
-    const size_t n_tr = trace ? B * ns * 8 : 0;
+    // outputs in pinned host memory are written by the kernel itself (no staging, no copy)
+    double*  m_tr = trace ? mapped(d->A_trace) : nullptr;
+    double*  m_Ae = endo ? mapped(d->A_end) : nullptr;
+    double*  m_Pm = pmax ? mapped(d->Pmax) : nullptr;
+    int32_t* m_st = mapped(d->status);
+    const size_t n_tr = (trace && !m_tr) ? B * ns * 8 : 0;
+    const size_t n_sched = (size_t)yaman4_scratch_bytes((int64_t)B);
 
     size_t need = Carver::need(B * 8) + Carver::need(n_g * 8) + Carver::need(n_a * 8) +
                   Carver::need(n_A0 * 8) + Carver::need(n_grid * 8) + Carver::need(n_tr * 8) +
-                  Carver::need(B * 64) + Carver::need(B * 32) + Carver::need(B * 4);
+                  Carver::need(B * 64) + Carver::need(B * 32) + Carver::need(B * 4) + Carver::need(n_sched);
     void* ws = nullptr;
     FPA_TRY(workspace(device, 0, need, &ws));
     cudaStream_t st;
@@ -284,6 +349,7 @@ int fpa_yaman4_rk4_batch_host(const fpa_yaman4_desc* d, int device) {
     double*  Aend  = cv.take<double>(B * 8);
     double*  Pm    = cv.take<double>(B * 4);
     int32_t* stat  = cv.take<int32_t>(B);
+    char*    sched = cv.take<char>(n_sched);
 
     FPA_TRY(up(dbeta, d->dbeta, B * 8, st));
     FPA_TRY(up(gam, d->gamma, n_g * 8, st));
@@ -297,10 +363,12 @@ int fpa_yaman4_rk4_batch_host(const fpa_yaman4_desc* d, int device) {
     dd.alpha   = alp;
     dd.A0      = A0;
     dd.z_grid  = d->z_grid ? grid : nullptr;
-    dd.A_trace = trace ? tr : nullptr;
-    dd.A_end   = endo ? Aend : nullptr;
-    dd.Pmax    = pmax ? Pm : nullptr;
-    dd.status  = stat;
+    dd.A_trace = trace ? (m_tr ? m_tr : tr) : nullptr;
+    dd.A_end   = endo ? (m_Ae ? m_Ae : Aend) : nullptr;
+    dd.Pmax    = pmax ? (m_Pm ? m_Pm : Pm) : nullptr;
+    dd.status  = d->status ? (m_st ? m_st : stat) : stat;
+    dd.scratch = sched;
+    dd.scratch_bytes = (int64_t)n_sched;
     if (d->gamma_stride == 0 && d->alpha_stride == 0) {  // host pointers: the broadcast values are known here
         dd.flags |= FPA_UNIFORM_PHYSICS;
         dd.gamma_uniform = d->gamma[0];
@@ -308,17 +376,62 @@ int fpa_yaman4_rk4_batch_host(const fpa_yaman4_desc* d, int device) {
     } else {
         dd.flags &= ~FPA_UNIFORM_PHYSICS;
     }
-    FPA_REQUIRE(!trace || d->A_trace, "FPA_OUT_TRACE needs A_trace");
-    FPA_REQUIRE(!pmax || d->Pmax, "FPA_OUT_PMAX needs Pmax");
-    FPA_REQUIRE(!endo || d->A_end, "FPA_OUT_END needs A_end");
     FPA_TRY(yaman4_launch(&dd, st));
-
-    if (trace) FPA_TRY(down(d->A_trace, tr, n_tr * 8, st));
-    if (endo) FPA_TRY(down(d->A_end, Aend, B * 64, st));
-    if (pmax) FPA_TRY(down(d->Pmax, Pm, B * 32, st));
-    FPA_TRY(down(d->status, stat, B * 4, st));
-    FPA_CUDA(cudaStreamSynchronize(st));
+    pb->st   = st;
+    pb->B    = B;
+    pb->n_tr = n_tr;
+    pb->user = *d;
+    pb->tr   = (trace && !m_tr) ? tr : nullptr;
+    pb->Ae   = (endo && !m_Ae) ? Aend : nullptr;
+    pb->Pm   = (pmax && !m_Pm) ? Pm : nullptr;
+    pb->stt  = (d->status && !m_st) ? stat : nullptr;
     return FPA_OK;
+}
+
+static int batch_host_collect(const PendingBatch& pb, int device) {
+    if (!pb.st) return FPA_OK;
+    FPA_TRY(use_device(device));
+    if (pb.tr) FPA_TRY(down(pb.user.A_trace, pb.tr, pb.n_tr * 8, pb.st));
+    if (pb.Ae) FPA_TRY(down(pb.user.A_end, pb.Ae, pb.B * 64, pb.st));
+    if (pb.Pm) FPA_TRY(down(pb.user.Pmax, pb.Pm, pb.B * 32, pb.st));
+    if (pb.stt) FPA_TRY(down(pb.user.status, pb.stt, pb.B * 4, pb.st));
+    return FPA_OK;
+}
+
+int fpa_yaman4_rk4_batch_host(const fpa_yaman4_desc* d, int device) {
+    PendingBatch pb;
+    FPA_TRY(batch_host_launch(d, device, &pb));
+    FPA_TRY(batch_host_collect(pb, device));
+    if (pb.st) FPA_CUDA(cudaStreamSynchronize(pb.st));
+    return FPA_OK;
+}
+
+int fpa_yaman4_rk4_batch_multi_host(const fpa_yaman4_desc* d, int n_devices, const int* devices) {
+    FPA_TRY(batch_host_check(d));
+    FPA_REQUIRE(n_devices >= 1 && n_devices <= 64 && devices != nullptr, "need 1..64 device ordinals");
+    if (n_devices == 1) return fpa_yaman4_rk4_batch_host(d, devices[0]);
+    const int64_t ns = fpa_n_saved(d->n_steps, d->save_every);
+    PendingBatch  pend[64];
+    return run_on_devices(
+        n_devices, devices, pend,
+        [&](int k, PendingBatch* pb) {
+            int64_t lo, hi;
+            balanced_range(d->n_points, n_devices, k, &lo, &hi);
+            *pb = PendingBatch();
+            if (hi <= lo) return (int)FPA_OK;
+            fpa_yaman4_desc part = *d;
+            part.n_points = hi - lo;
+            part.dbeta    = d->dbeta + lo;
+            part.gamma    = d->gamma + lo * d->gamma_stride;
+            part.alpha    = d->alpha + lo * d->alpha_stride;
+            part.A0       = d->A0 + lo * d->A0_stride * 8;
+            if (d->A_trace) part.A_trace = d->A_trace + lo * ns * 8;
+            if (d->A_end) part.A_end = d->A_end + lo * 8;
+            if (d->Pmax) part.Pmax = d->Pmax + lo * 4;
+            if (d->status) part.status = d->status + lo;
+            return batch_host_launch(&part, devices[k], pb);
+        },
+        batch_host_collect);
 }
 
 int fpa_yaman4_rhs_host(int64_t B, const double* z, const double* A, const double* gamma,
@@ -403,9 +516,12 @@ int fpa_dbeta_table_host(const fpa_plan_desc* d, int device) {
 }
 
 // ------------------------------------------------------------------ fused sweep
+int64_t fpa_yaman4_scratch_bytes(int64_t n_points) { return yaman4_scratch_bytes(n_points); }
+
 int64_t fpa_yaman4_sweep_scratch_bytes(int64_t n_points) {
-    (void)n_points;
-    return 0;  // the fused sweep kernel needs no workspace (kept for ABI stability)
+    // scheduler counters + one state record per point for the z-segment scheduler (csrc/yaman4.cu); a
+    // sweep launched without it (scratch == NULL) runs as the whole-run kernel
+    return yaman4_scratch_bytes(n_points);
 }
 
 int fpa_yaman4_sweep_dev(const fpa_sweep_desc* d, void* scratch, int64_t scratch_bytes, void* stream) {
@@ -413,9 +529,7 @@ int fpa_yaman4_sweep_dev(const fpa_sweep_desc* d, void* scratch, int64_t scratch
         set_error("no CUDA device is visible: libfpa_b200 has no CPU path");
         return FPA_ERR_NO_DEVICE;
     }
-    (void)scratch;
-    (void)scratch_bytes;
-    return sweep_dev(d, static_cast<cudaStream_t>(stream));
+    return sweep_dev(d, scratch, scratch_bytes, static_cast<cudaStream_t>(stream));
 }
 
 // One sweep with host pointers in two steps, so that several devices can be driven from one thread:
@@ -438,15 +552,21 @@ static int sweep_host_launch(const fpa_sweep_desc* d, int device, PendingSweep* 
     FPA_REQUIRE(pl.lambda1 && pl.lambda2 && pl.lambda3, "wavelength axes must be set");
     FPA_TRY(use_device(device));
     *ps = PendingSweep();
-    const size_t n1 = (size_t)pl.n1, n3 = (size_t)pl.n3, B = n1 * n3;
+    const size_t n1 = (size_t)pl.n1, n3 = (size_t)pl.n3;
+    FPA_REQUIRE(d->first_point >= 0 && d->n_sub_points >= 0 &&
+                    (size_t)(d->first_point + d->n_sub_points) <= n1 * n3,
+                "first_point / n_sub_points must select a range of the n1*n3 grid");
+    // points of this call: the whole grid, or the sub-range (outputs are indexed from its first point)
+    const size_t B = (d->first_point == 0 && d->n_sub_points == 0) ? n1 * n3 : (size_t)d->n_sub_points;
     if (B == 0) return FPA_OK;
     FPA_REQUIRE(d->gain_lin != nullptr, "gain_lin must be set");
     const size_t n2 = pl.lambda2_stride ? n1 : 1;
+    const size_t n_sched = (size_t)yaman4_scratch_bytes((int64_t)B);
     size_t need = Carver::need(n1 * 8) + Carver::need(n2 * 8) + Carver::need(n3 * 8) +
                   Carver::need(B * 8) /*gain*/ + Carver::need(B * 8) /*dbeta*/ +
                   Carver::need(B * 4) /*valid*/ + Carver::need(B * 4) /*status*/ +
                   Carver::need(B * 32) /*Pmax*/ + Carver::need(B * 64) /*A_end*/ +
-                  Carver::need(B * 32) /*omega*/;
+                  Carver::need(B * 32) /*omega*/ + Carver::need(n_sched);
     void* ws = nullptr;
     FPA_TRY(workspace(device, 3, need, &ws));
     cudaStream_t st;
@@ -463,6 +583,7 @@ static int sweep_host_launch(const fpa_sweep_desc* d, int device, PendingSweep* 
     double*  Pm   = cv.take<double>(B * 4);
     double*  Ae   = cv.take<double>(B * 8);
     double*  om   = cv.take<double>(B * 4);
+    char*    sched = cv.take<char>(n_sched);
 
     FPA_TRY(up(l1, pl.lambda1, n1 * 8, st));
     FPA_TRY(up(l2, pl.lambda2, n2 * 8, st));
@@ -488,7 +609,7 @@ static int sweep_host_launch(const fpa_sweep_desc* d, int device, PendingSweep* 
     dd.Pmax         = d->Pmax ? (m_Pm ? m_Pm : Pm) : nullptr;
     dd.A_end        = d->A_end ? (m_Ae ? m_Ae : Ae) : nullptr;
     dd.status       = m_st ? m_st : stt;
-    FPA_TRY(sweep_dev(&dd, st));
+    FPA_TRY(sweep_dev(&dd, sched, (int64_t)n_sched, st));
     ps->st   = st;
     ps->B    = B;
     ps->user = *d;
@@ -529,49 +650,31 @@ int fpa_yaman4_sweep_multi_host(const fpa_sweep_desc* d, int n_devices, const in
     FPA_REQUIRE(n_devices >= 1 && n_devices <= 64 && devices != nullptr, "need 1..64 device ordinals");
     const int64_t n1 = d->plan.n1, n3 = d->plan.n3;
     FPA_REQUIRE(n1 >= 0 && n3 >= 0, "grid sizes must be >= 0");
+    FPA_REQUIRE(d->first_point == 0 && d->n_sub_points == 0, "the multi-device sweep splits the whole grid itself");
     if (n_devices == 1) return fpa_yaman4_sweep_host(d, devices[0]);
-    // contiguous row ranges, ceil(n1 / n_devices) rows each (the last ones may be short or empty)
-    const int64_t per = (n1 + n_devices - 1) / n_devices;
-    PendingSweep  pend[64];
-    bool          collected[64] = {};
-    int           used = 0, rc = FPA_OK;
-    for (int k = 0; k < n_devices && rc == FPA_OK; ++k) {       // every kernel in flight first ...
-        const int64_t r0 = (int64_t)k * per < n1 ? (int64_t)k * per : n1;
-        const int64_t r1 = r0 + per < n1 ? r0 + per : n1;
-        used = k + 1;
-        if (r1 <= r0) continue;
-        fpa_sweep_desc part = *d;
-        const int64_t  off = r0 * n3;
-        part.plan.n1      = r1 - r0;
-        part.plan.lambda1 = d->plan.lambda1 + r0;
-        part.plan.lambda2 = d->plan.lambda2 + r0 * d->plan.lambda2_stride;
-        if (d->plan.omega) part.plan.omega = d->plan.omega + off * 4;
-        if (d->plan.dbeta) part.plan.dbeta = d->plan.dbeta + off;
-        if (d->plan.valid) part.plan.valid = d->plan.valid + off;
-        if (d->gain_lin) part.gain_lin = d->gain_lin + off;
-        if (d->Pmax) part.Pmax = d->Pmax + off * 4;
-        if (d->A_end) part.A_end = d->A_end + off * 8;
-        if (d->status) part.status = d->status + off;
-        // a device that is listed twice shares one workspace and stream: queue the earlier part's
-        // copies before the next kernel may overwrite the staging buffers
-        for (int j = 0; j < k && rc == FPA_OK; ++j) {
-            if (devices[j] == devices[k] && pend[j].st && !collected[j]) {
-                rc = sweep_host_collect(pend[j], devices[j]);
-                collected[j] = true;
-            }
-        }
-        if (rc == FPA_OK) rc = sweep_host_launch(&part, devices[k], &pend[k]);
-    }
-    for (int k = 0; k < used && rc == FPA_OK; ++k)               // ... then the copies
-        if (!collected[k]) rc = sweep_host_collect(pend[k], devices[k]);
-    // wait for everything that was queued, also after an error on a later device
-    for (int k = 0; k < used; ++k) {
-        if (!pend[k].st) continue;
-        if (cudaSetDevice(devices[k]) != cudaSuccess || cudaStreamSynchronize(pend[k].st) != cudaSuccess) {
-            if (rc == FPA_OK) rc = cuda_fail(cudaGetLastError(), "fpa_yaman4_sweep_multi_host: stream synchronize");
-        }
-    }
-    return rc;
+    // contiguous ranges of the FLATTENED grid, sizes differing by at most one: a 1-D sweep (n1 = 1) or a
+    // grid with fewer pump rows than devices still uses every device
+    PendingSweep pend[64];
+    return run_on_devices(
+        n_devices, devices, pend,
+        [&](int k, PendingSweep* ps) {
+            int64_t lo, hi;
+            balanced_range(n1 * n3, n_devices, k, &lo, &hi);
+            *ps = PendingSweep();
+            if (hi <= lo) return (int)FPA_OK;
+            fpa_sweep_desc part = *d;
+            part.first_point  = lo;
+            part.n_sub_points = hi - lo;
+            if (d->plan.omega) part.plan.omega = d->plan.omega + lo * 4;
+            if (d->plan.dbeta) part.plan.dbeta = d->plan.dbeta + lo;
+            if (d->plan.valid) part.plan.valid = d->plan.valid + lo;
+            if (d->gain_lin) part.gain_lin = d->gain_lin + lo;
+            if (d->Pmax) part.Pmax = d->Pmax + lo * 4;
+            if (d->A_end) part.A_end = d->A_end + lo * 8;
+            if (d->status) part.status = d->status + lo;
+            return sweep_host_launch(&part, devices[k], ps);
+        },
+        sweep_host_collect);
 }
 
 // ------------------------------------------------------------------ linear test RHS
@@ -724,6 +827,22 @@ int fpa_host_alloc(void** ptr, int64_t bytes) {
 int fpa_host_free(void* ptr) {
     if (ptr == nullptr) return FPA_OK;
     FPA_CUDA(cudaFreeHost(ptr));
+    return FPA_OK;
+}
+
+int fpa_host_register(void* ptr, int64_t bytes) {
+    FPA_REQUIRE(ptr != nullptr && bytes > 0, "bad arguments");
+    if (fpa_device_count() <= 0) {
+        set_error("no CUDA device is visible: page-locking host memory needs the CUDA runtime");
+        return FPA_ERR_NO_DEVICE;
+    }
+    FPA_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return FPA_OK;
+}
+
+int fpa_host_unregister(void* ptr) {
+    if (ptr == nullptr) return FPA_OK;
+    FPA_CUDA(cudaHostUnregister(ptr));
     return FPA_OK;
 }
 

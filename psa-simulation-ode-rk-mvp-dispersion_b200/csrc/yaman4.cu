@@ -32,6 +32,8 @@
 //    structure step by step (h_i by subtraction, sincos at z, z+h/2, z+h, k_j formed, y + h/6*(..)).
 #include "plan_point.cuh"
 
+#include <stdlib.h>
+
 namespace fpa {
 
 constexpr int kResync = 32;  // steps between exact sincos re-synchronisations of the phase
@@ -200,28 +202,36 @@ __device__ __forceinline__ void write_results(const Yaman4Params& p, int64_t b, 
     }
 }
 
-// The z-loop of the fast path: advances y over all steps, keeps the running maxima in pm and
-// returns the first step whose result was not finite (or FPA_POINT_OK).
-template <bool TRACE, bool PMAX, bool LOSS>
+// The z-loop of the fast path: advances y over the steps [i0, i1) of the run, keeps the running maxima
+// in pm and returns the first step whose result was not finite (or `bad` as given).  The whole run is
+// (0, n_steps); the z-segment scheduler (SegParams below) calls it once per segment with the
+// state, pm and bad of the previous segment.  i0 must be a multiple of kResync: the phase factor is
+// rebuilt by the exact sincos at the first step of the range, exactly where the whole-run loop rebuilds
+// it, so a segmented run is bit-identical to a whole one.
+template <bool TRACE, bool PMAX, bool LOSS, bool SEG = false>
 __device__ __forceinline__ int32_t fast_integrate(const Yaman4Params& p, int64_t b, double dbeta,
-                                                  const Yaman4Coef& cf, double (&y)[8], double (&pm)[4]) {
+                                                  const Yaman4Coef& cf, double (&y)[8], double (&pm)[4],
+                                                  int i0_in = 0, int i1_in = 0, int32_t bad_in = FPA_POINT_OK) {
+    const int i0 = SEG ? i0_in : 0;
+    const int i1 = SEG ? i1_in : p.n_steps;
     double* tr = nullptr;
-    if (TRACE) tr = p.A_trace + b * p.n_saved * 8;
-    if (PMAX) {
+    if (TRACE) tr = p.A_trace + b * p.n_saved * 8 + (i0 == 0 ? 0 : ((int64_t)(i0 / p.save_every) + 1) * 8);
+    if (i0 == 0) {
+        if (PMAX) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pm[j] = -1.0;  // |A|^2 >= 0: first sample always replaces it
+            for (int j = 0; j < 4; ++j) pm[j] = -1.0;  // |A|^2 >= 0: first sample always replaces it
+        }
+        save_sample(y, tr, pm, TRACE, PMAX);
     }
-    save_sample(y, tr, pm, TRACE, PMAX);
 
-    const int    n_steps = p.n_steps;
     const double h = p.h, z0 = p.z0;
     // rotation by half a step
     double rr, ri;
     sincos(dbeta * (0.5 * h), &ri, &rr);
 
     double  qr = cf.q0, qi = 0.0;  // (h/2)*2*gamma*exp(i*dbeta*z_i)
-    int     save_ctr = p.save_every;
-    int32_t bad = FPA_POINT_OK;
+    int     save_ctr = SEG ? p.save_every - (i0 % p.save_every) : p.save_every;
+    int32_t bad = SEG ? bad_in : FPA_POINT_OK;
     // Weights of the stage states in y' = -y/3 + ys2/3 + 2 ys3/3 + ys4/3 + (h/6) f(ys4).  They must sum
     // to EXACTLY one in floating point: fl(1/3) + fl(2/3) = 1 - 2^-54 shrinks |A| by that factor every
     // step (and fl(1/3) + fl(1 - fl(1/3)) = 1 + 2^-54 grows it), and the Kerr phase integrates the
@@ -230,7 +240,7 @@ __device__ __forceinline__ int32_t fast_integrate(const Yaman4Params& p, int64_t
     // third_c = 1 - fl(2/3) makes two_thirds + third_c == 1 with no rounding.
     const double third = 1.0 / 3.0, two_thirds = 2.0 / 3.0, third_c = 1.0 - two_thirds;
 
-    for (int i = 0; i < n_steps; ++i) {
+    for (int i = i0; i < i1; ++i) {
         if ((i & (kResync - 1)) == 0) {
             double s, c;
             sincos(dbeta * fma((double)i, h, z0), &s, &c);
@@ -305,6 +315,112 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_fast_kernel(const 
     write_results(p, b, y, pm, PMAX, bad);
 }
 
+// ------------------------------------------------------------------ z-segment scheduler
+// The integrators as PERSISTENT kernels for batches of one wave or more.  Every point costs the same, so a
+// batch of 1.65 waves (125 000 points per GPU when the 1e6-point grid is split over 8 GPUs) runs as one
+// full wave plus a second wave at 65 % occupancy that takes nearly as long: the sub-partition with the
+// most warps sets the time.  Here the fiber is cut into segments of seg_steps RK4 steps and the work
+// items (warp of 32 points, segment) are handed out in segment-major order from one atomic counter to
+// the resident warps: the chip stays full until the last seg_steps of the last item, so the tail costs
+// at most one segment instead of one wave.  Between segments a point's state (y, running maxima, first
+// bad step, its Delta-beta: 14 doubles + 1 int, SoA) goes through global memory -- 116 B per point per
+// segment, L2-resident -- and done[w] counts the finished segments of warp-item w (release / acquire).
+// When item t is handed out at most R-1 older items (R = resident warps) can still be running, and the
+// launcher only segments batches of n_warps >= R items per segment, so the item t depends on, t - n_warps,
+// is normally finished: the acquire loop is a correctness guard, not a wait.  Segment boundaries are
+// multiples of kResync steps, which makes the arithmetic -- phase re-synchronisation, save schedule,
+// finite check -- identical to the whole-run loop: results are bit-identical to the whole-run kernels.
+struct SegParams {
+    unsigned int* counter;    // [1] next work item (zeroed by the launcher)
+    int*          done;       // [n_warps] finished segments per warp-item (zeroed by the launcher)
+    double*       state;      // [kSegDoubles][n_pad]
+    int32_t*      bad;        // [n_pad]
+    int64_t       n_pad;      // n_warps * 32
+    int           n_warps, n_seg, seg_steps;
+};
+constexpr int kSegDoubles = 13;  // y[8], pm[4], dbeta
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Next work item of the z-segment scheduler for this warp: (segment, warp-item), or false when the queue
+// is empty.  Waits (normally zero iterations) until the item's previous segment has been published.
+__device__ __forceinline__ bool seg_next_item(const SegParams& g, int lane, int& seg, int& w) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(g.counter, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= (unsigned)g.n_warps * (unsigned)g.n_seg) return false;
+    seg = (int)(t / (unsigned)g.n_warps);
+    w   = (int)(t - (unsigned)seg * (unsigned)g.n_warps);
+    if (seg > 0) {
+        while (ld_acquire(g.done + w) < seg) __nanosleep(100);
+    }
+    return true;
+}
+
+__device__ __forceinline__ void seg_publish(const SegParams& g, int lane, int seg, int w) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(g.done + w, seg + 1);
+}
+
+// The batch integrator through the z-segment scheduler:
+// same arithmetic as yaman4_fast_kernel, bit-identical results.  Uniform physics only (UNIFORM = 1 | 2).
+template <bool TRACE, bool PMAX, int UNIFORM, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_fast_seg_kernel(const Yaman4Params p, const SegParams g) {
+    const int lane = threadIdx.x & 31;
+    int       seg, w;
+    while (seg_next_item(g, lane, seg, w)) {
+        const int64_t b = (int64_t)w * 32 + lane;
+        const bool    last = seg == g.n_seg - 1;
+        if (b < p.n_points) {
+            const double dbeta = p.dbeta[b];
+            double       y[8], pm[4] = {0.0, 0.0, 0.0, 0.0};
+            int32_t      bad = FPA_POINT_OK;
+            double* const st = g.state + b;
+            if (nonfinite(dbeta)) {
+                if (seg == 0) {
+                    load_state(p, b, y);
+                    write_invalid_point(p, b, y);
+                }
+            } else {
+                if (seg == 0) {
+                    load_state(p, b, y);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = __ldcg(st + j * g.n_pad);
+                    if (PMAX) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pm[j] = __ldcg(st + (8 + j) * g.n_pad);
+                    }
+                    bad = __ldcg(g.bad + b);
+                }
+                const int i0 = seg * g.seg_steps;
+                const int i1 = last ? p.n_steps : i0 + g.seg_steps;
+                bad = fast_integrate<TRACE, PMAX, UNIFORM != 2, true>(p, b, dbeta, p.coef, y, pm, i0, i1, bad);
+                if (last) {
+                    write_results(p, b, y, pm, PMAX, bad);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) __stcg(st + j * g.n_pad, y[j]);
+                    if (PMAX) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) __stcg(st + (8 + j) * g.n_pad, pm[j]);
+                    }
+                    __stcg(g.bad + b, bad);
+                }
+            }
+        }
+        if (!last) seg_publish(g, lane, seg, w);
+    }
+}
+
 // ------------------------------------------------------------------ fused sweep
 // ONE kernel per sweep: per scan point the prologue builds the frequency plan, the validity flag
 // and Delta-beta (plan_point.cuh), the body is the fast RK4 loop above, and the epilogue reduces
@@ -320,18 +436,18 @@ struct SweepExtra {
     double     A0[8];
     double     p_signal;
     double*    gain_lin;    // [B]
+    int64_t    first_point; // grid index of point 0 of this launch (sub-range sweeps; outputs are indexed locally)
 };
 
-template <bool LOSS, int THREADS, int MIN_BLOCKS>
-__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_sweep_kernel(const Yaman4Params p, const SweepExtra x) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.n_points) return;
-    const int64_t i1 = b / x.plan.n3, i3 = b - i1 * x.plan.n3;
-
+// Prologue of one scan point: frequency plan, validity, reported and integration Delta-beta; writes the
+// plan outputs.  Returns false for points the reference's per-point try/except turns into NaN.
+__device__ __forceinline__ bool sweep_prologue(const SweepExtra& x, int64_t b, double& db_run) {
+    const int64_t bg = b + x.first_point;
+    const int64_t i1 = bg / x.plan.n3, i3 = bg - i1 * x.plan.n3;
     double w[4];
     bool   ok = plan_omegas(x.plan.lambda1[i1], x.plan.lambda2[i1 * x.plan.lambda2_stride], x.plan.lambda3[i3], w);
     const double db_report = plan_dbeta(x.plan, x.plan.beta, x.plan.provided, w, ok);
-    double       db_run = db_report;
+    db_run = db_report;
     if (!x.same_run) {
         bool ok_run = ok;
         db_run = plan_dbeta(x.plan, x.beta_run, x.provided_run, w, ok_run);
@@ -344,45 +460,119 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_sweep_kernel(const
         o[0] = make_double2(w[0], w[1]);
         o[1] = make_double2(w[2], w[3]);
     }
+    return ok && !nonfinite(db_run);
+}
 
+// the reference's per-point try/except leaves NaN (scan_mismtach.py:736-738)
+__device__ __forceinline__ void sweep_invalid(const Yaman4Params& p, const SweepExtra& x, int64_t b) {
+    const double qn = qnan();
+    if (p.A_end)
+        for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, qn, qn);
+    if (p.Pmax)
+        for (int j = 0; j < 4; ++j) p.Pmax[b * 4 + j] = qn;
+    if (p.status) p.status[b] = p.check ? 0 : FPA_POINT_OK;
+    x.gain_lin[b] = qn;
+}
+
+// Epilogue of an integrated point: status, optional end state / maxima, and the sweep's gain metric.
+__device__ __forceinline__ void sweep_epilogue(const Yaman4Params& p, const SweepExtra& x, int64_t b,
+                                               const double (&y)[8], const double (&pm)[4], int32_t bad) {
+    if (p.check && bad == FPA_POINT_OK) {
+        bool nf = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nf |= nonfinite(y[j]);
+        if (nf) bad = p.n_steps - 1;
+    }
+    if (p.status) p.status[b] = p.check ? bad : FPA_POINT_OK;
+    if (p.A_end) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, y[2 * j], y[2 * j + 1]);
+    }
+    if (p.Pmax) {
+        double2* o = reinterpret_cast<double2*>(p.Pmax + b * 4);
+        o[0] = make_double2(pm[0], pm[1]);
+        o[1] = make_double2(pm[2], pm[3]);
+    }
+    // gain = max_saved |A3|^2 / p_in[2]; NaN for failed, non-finite or <= 0 (scan_mismtach.py:723-734)
+    double gain = qnan();
+    if (!(p.check && bad != FPA_POINT_OK) && !nonfinite(pm[2])) {
+        const double q = pm[2] / x.p_signal;
+        if (!nonfinite(q) && q > 0.0) gain = q;
+    }
+    x.gain_lin[b] = gain;
+}
+
+template <bool LOSS, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) yaman4_sweep_kernel(const Yaman4Params p, const SweepExtra x) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.n_points) return;
+    double db_run;
+    if (!sweep_prologue(x, b, db_run)) {
+        sweep_invalid(p, x, b);
+        return;
+    }
     double y[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) y[j] = x.A0[j];
-    double gain = qnan();
-    if (!ok || nonfinite(db_run)) {
-        // the reference's per-point try/except leaves NaN (scan_mismtach.py:736-738)
-        const double qn = qnan();
-        if (p.A_end)
-            for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, qn, qn);
-        if (p.Pmax)
-            for (int j = 0; j < 4; ++j) p.Pmax[b * 4 + j] = qn;
-        if (p.status) p.status[b] = p.check ? 0 : FPA_POINT_OK;
-    } else {
-        double  pm[4] = {0.0, 0.0, 0.0, 0.0};
-        int32_t bad = fast_integrate<false, true, LOSS>(p, b, db_run, p.coef, y, pm);
-        if (p.check && bad == FPA_POINT_OK) {
-            bool nf = false;
+    double        pm[4] = {0.0, 0.0, 0.0, 0.0};
+    const int32_t bad = fast_integrate<false, true, LOSS>(p, b, db_run, p.coef, y, pm);
+    sweep_epilogue(p, x, b, y, pm, bad);
+}
+
+// ------------------------------------------------------------------ fused sweep, z-segment scheduler
+// The sweep kernel above as a persistent kernel on the z-segment scheduler: prologue at segment 0, gain
+// epilogue at the last segment, the point's integration Delta-beta travels with its state.
+template <bool LOSS, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+    yaman4_sweep_seg_kernel(const Yaman4Params p, const SweepExtra x, const SegParams g) {
+    const int lane = threadIdx.x & 31;
+    int       seg, w;
+    while (seg_next_item(g, lane, seg, w)) {
+        const int64_t b = (int64_t)w * 32 + lane;
+        const bool    last = seg == g.n_seg - 1;
+        if (b < p.n_points) {
+            double  y[8], pm[4] = {0.0, 0.0, 0.0, 0.0}, db_run;
+            int32_t bad = FPA_POINT_OK;
+            bool    run;
+            double* const st = g.state + b;
+            if (seg == 0) {
+                run = sweep_prologue(x, b, db_run);
+                if (!run) {
+                    sweep_invalid(p, x, b);
+                    db_run = qnan();
+                }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) nf |= nonfinite(y[j]);
-            if (nf) bad = p.n_steps - 1;
-        }
-        if (p.status) p.status[b] = p.check ? bad : FPA_POINT_OK;
-        if (p.A_end) {
+                for (int j = 0; j < 8; ++j) y[j] = x.A0[j];
+            } else {
+                db_run = __ldcg(st + 12 * g.n_pad);
+                run = !nonfinite(db_run);
+                if (run) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) store_c128(p.A_end + b * 8 + 2 * j, y[2 * j], y[2 * j + 1]);
+                    for (int j = 0; j < 8; ++j) y[j] = __ldcg(st + j * g.n_pad);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pm[j] = __ldcg(st + (8 + j) * g.n_pad);
+                    bad = __ldcg(g.bad + b);
+                }
+            }
+            if (run) {
+                const int i0 = seg * g.seg_steps;
+                const int i1 = last ? p.n_steps : i0 + g.seg_steps;
+                bad = fast_integrate<false, true, LOSS, true>(p, b, db_run, p.coef, y, pm, i0, i1, bad);
+                if (last) sweep_epilogue(p, x, b, y, pm, bad);
+            }
+            if (!last) {
+                __stcg(st + 12 * g.n_pad, db_run);
+                if (run) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) __stcg(st + j * g.n_pad, y[j]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) __stcg(st + (8 + j) * g.n_pad, pm[j]);
+                    __stcg(g.bad + b, bad);
+                }
+            }
         }
-        if (p.Pmax) {
-            double2* o = reinterpret_cast<double2*>(p.Pmax + b * 4);
-            o[0] = make_double2(pm[0], pm[1]);
-            o[1] = make_double2(pm[2], pm[3]);
-        }
-        // gain = max_saved |A3|^2 / p_in[2]; NaN for failed, non-finite or <= 0 (scan_mismtach.py:723-734)
-        if (!(p.check && bad != FPA_POINT_OK) && !nonfinite(pm[2])) {
-            const double q = pm[2] / x.p_signal;
-            if (!nonfinite(q) && q > 0.0) gain = q;
-        }
+        if (!last) seg_publish(g, lane, seg, w);
     }
-    x.gain_lin[b] = gain;
 }
 
 // ------------------------------------------------------------------ exact path
@@ -506,18 +696,93 @@ __global__ void yaman4_rhs_kernel(int64_t B, const double* z, const double* A, c
 constexpr int kFastThreads = FPA_YAMAN4_THREADS, kFastMinBlocks = FPA_YAMAN4_MIN_BLOCKS;
 // the fused sweep kernel gets its best schedule (fewest 3-register FMAs, tools/sass_cost.py) at 4
 constexpr int kSweepMinBlocks = 4;
+// z-segment scheduler: RK4 steps per segment (multiples of kResync), chosen by measurement
+// (profiles/r2_seg_tune.txt): 64 below two waves of the resident warps, 128 above -- with those the
+// scheduler is at least as fast as the whole-run kernel at every batch of one wave or more
+// (1.00 waves 68 -> 83 % of the FP64 peak, 1.65 waves 80.8 -> 86.2 %, 13.2 waves 87.2 -> 87.3 %).
+constexpr int kSegStepsShort = 64, kSegStepsLong = 128;
+
+// ---- z-segment scheduler: scratch layout and launch geometry
+static size_t seg_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int64_t yaman4_scratch_bytes(int64_t n_points) {
+    if (n_points <= 0) return 0;
+    const size_t n_warps = (size_t)((n_points + 31) / 32), n_pad = n_warps * 32;
+    return (int64_t)(256 + seg_align(n_warps * sizeof(int)) + seg_align(n_pad * kSegDoubles * sizeof(double)) +
+                     seg_align(n_pad * sizeof(int32_t)));
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// CTAs of a persistent kernel that are resident at once on the current device.
+template <typename Kernel>
+static int resident_ctas(Kernel kernel, int threads) {
+    int dev = 0, sms = 148, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    return sms * (per_sm < 1 ? 1 : per_sm);
+}
+
+// Decides whether a batch runs through the scheduler and, if so, fills `g` and clears its counters.
+// Legal when the caller gave enough scratch, every segment holds at least one item per resident warp
+// (then an item's predecessor is finished when it is handed out) and the run has at least two segments.
+// FPA_SWEEP_SEG=0 forces the whole-run kernels, FPA_SWEEP_SEG_STEPS overrides the segment length (tools, tests).
+static int seg_plan(int64_t B, int64_t n_steps, int ctas, int threads, void* scratch, int64_t scratch_bytes,
+                    cudaStream_t st, SegParams& g, bool& use_seg) {
+    const int64_t n_warps = (B + 31) / 32, resident_warps = (int64_t)ctas * (threads / 32);
+    int seg_steps = env_int("FPA_SWEEP_SEG_STEPS", n_warps < 2 * resident_warps ? kSegStepsShort : kSegStepsLong);
+    seg_steps = (seg_steps + kResync - 1) / kResync * kResync;
+    if (seg_steps < kResync) seg_steps = kResync;
+    use_seg = env_int("FPA_SWEEP_SEG", 1) != 0 && scratch != nullptr && scratch_bytes >= yaman4_scratch_bytes(B) &&
+              n_warps >= resident_warps && n_steps >= 2 * (int64_t)seg_steps &&
+              n_warps * ((n_steps + seg_steps - 1) / seg_steps) < 4000000000LL;
+    if (!use_seg) return FPA_OK;
+    char* base = static_cast<char*>(scratch);
+    g.counter   = reinterpret_cast<unsigned int*>(base);
+    g.done      = reinterpret_cast<int*>(base + 256);
+    g.state     = reinterpret_cast<double*>(base + 256 + seg_align((size_t)n_warps * sizeof(int)));
+    g.n_pad     = n_warps * 32;
+    g.bad       = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(g.state) +
+                                             seg_align((size_t)g.n_pad * kSegDoubles * sizeof(double)));
+    g.n_warps   = (int)n_warps;
+    g.seg_steps = seg_steps;
+    g.n_seg     = (int)((n_steps + seg_steps - 1) / seg_steps);
+    FPA_CUDA(cudaMemsetAsync(base, 0, 256 + (size_t)n_warps * sizeof(int), st));
+    return FPA_OK;
+}
 
 template <bool TRACE, bool PMAX>
-static cudaError_t launch_fast(const Yaman4Params& p, bool uniform, cudaStream_t st) {
+static int launch_fast(const Yaman4Params& p, bool uniform, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
     const int  threads = kFastThreads;
     const long blocks  = (long)((p.n_points + threads - 1) / threads);
+    if (uniform) {  // the z-segment scheduler carries the uniform-physics instantiations
+        SegParams g;
+        bool      use_seg = false;
+        const int ctas = p.lossless ? resident_ctas(yaman4_fast_seg_kernel<TRACE, PMAX, 2, kFastThreads, kFastMinBlocks>, threads)
+                                    : resident_ctas(yaman4_fast_seg_kernel<TRACE, PMAX, 1, kFastThreads, kFastMinBlocks>, threads);
+        int       rc = seg_plan(p.n_points, p.n_steps, ctas, threads, scratch, scratch_bytes, st, g, use_seg);
+        if (rc != FPA_OK) return rc;
+        if (use_seg) {
+            if (p.lossless)
+                yaman4_fast_seg_kernel<TRACE, PMAX, 2, kFastThreads, kFastMinBlocks><<<ctas, threads, 0, st>>>(p, g);
+            else
+                yaman4_fast_seg_kernel<TRACE, PMAX, 1, kFastThreads, kFastMinBlocks><<<ctas, threads, 0, st>>>(p, g);
+            FPA_CUDA(cudaGetLastError());
+            return FPA_OK;
+        }
+    }
     if (uniform && p.lossless)
         yaman4_fast_kernel<TRACE, PMAX, 2, kFastThreads, kFastMinBlocks><<<blocks, threads, 0, st>>>(p);
     else if (uniform)
         yaman4_fast_kernel<TRACE, PMAX, 1, kFastThreads, kFastMinBlocks><<<blocks, threads, 0, st>>>(p);
     else
         yaman4_fast_kernel<TRACE, PMAX, 0, kFastThreads, kFastMinBlocks><<<blocks, threads, 0, st>>>(p);
-    return cudaGetLastError();
+    FPA_CUDA(cudaGetLastError());
+    return FPA_OK;
 }
 
 int yaman4_launch(const fpa_yaman4_desc* d, cudaStream_t st) {
@@ -564,38 +829,41 @@ int yaman4_launch(const fpa_yaman4_desc* d, cudaStream_t st) {
     p.coef         = make_coef(uniform ? d->gamma_uniform : 0.0, uniform ? d->alpha_uniform : 0.0, p.h);
     p.lossless     = (uniform && d->alpha_uniform == 0.0) ? 1 : 0;
 
-    cudaError_t  e;
     const int    threads = 128;
     const long   blocks  = (long)((p.n_points + threads - 1) / threads);
-    if (d->z_grid) {
-        yaman4_exact_kernel<true><<<blocks, threads, 0, st>>>(p);
-        e = cudaGetLastError();
-    } else if (d->flags & FPA_PHASE_EXACT) {
-        yaman4_exact_kernel<false><<<blocks, threads, 0, st>>>(p);
-        e = cudaGetLastError();
-    } else if (trace && pmax) {
-        e = launch_fast<true, true>(p, uniform, st);
-    } else if (trace) {
-        e = launch_fast<true, false>(p, uniform, st);
-    } else if (pmax) {
-        e = launch_fast<false, true>(p, uniform, st);
-    } else {
-        e = launch_fast<false, false>(p, uniform, st);
+    if (d->z_grid || (d->flags & FPA_PHASE_EXACT)) {
+        if (d->z_grid)
+            yaman4_exact_kernel<true><<<blocks, threads, 0, st>>>(p);
+        else
+            yaman4_exact_kernel<false><<<blocks, threads, 0, st>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "yaman4_exact_kernel launch");
+        return FPA_OK;
     }
-    if (e != cudaSuccess) return cuda_fail(e, "yaman4 kernel launch");
-    return FPA_OK;
+    if (trace && pmax) return launch_fast<true, true>(p, uniform, d->scratch, d->scratch_bytes, st);
+    if (trace) return launch_fast<true, false>(p, uniform, d->scratch, d->scratch_bytes, st);
+    if (pmax) return launch_fast<false, true>(p, uniform, d->scratch, d->scratch_bytes, st);
+    return launch_fast<false, false>(p, uniform, d->scratch, d->scratch_bytes, st);
 }
 
 // plan: the sweep's plan descriptor (device axis pointers); run_scale = 1 or 1000 (length unit);
 // gamma/alpha/z_max/dz per length unit, exactly as fpa_sweep_desc carries them.
 int plan_fill(const fpa_plan_desc* d, PlanParams& p);
 
-int yaman4_sweep_launch(const fpa_sweep_desc* d, cudaStream_t st) {
+int yaman4_sweep_launch(const fpa_sweep_desc* d, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
     FPA_REQUIRE(d != nullptr, "sweep descriptor is NULL");
+    if (d->flags & FPA_PHASE_EXACT) {
+        set_error("FPA_PHASE_EXACT is not available for the fused sweep: build the table with fpa_dbeta_table_* "
+                  "and integrate with fpa_yaman4_rk4_batch_* (which honours the flag)");
+        return FPA_ERR_UNSUPPORTED;
+    }
     SweepExtra x;
     int rc = plan_fill(&d->plan, x.plan);
     if (rc != FPA_OK) return rc;
-    const int64_t B = d->plan.n1 * d->plan.n3;
+    const int64_t grid = d->plan.n1 * d->plan.n3;
+    FPA_REQUIRE(d->first_point >= 0 && d->n_sub_points >= 0 && d->first_point + d->n_sub_points <= grid,
+                "first_point / n_sub_points must select a range of the n1*n3 grid");
+    const int64_t B = (d->first_point == 0 && d->n_sub_points == 0) ? grid : d->n_sub_points;
     FPA_REQUIRE(d->gain_lin != nullptr || B == 0, "gain_lin must be set");
     FPA_REQUIRE(d->length_scale == 1.0 || d->length_scale == 1000.0, "length_scale must be 1 or 1000");
     FPA_REQUIRE(d->z_max > 0.0, "z_max must be positive");
@@ -613,6 +881,7 @@ int yaman4_sweep_launch(const fpa_sweep_desc* d, cudaStream_t st) {
     for (int j = 0; j < 8; ++j) x.A0[j] = d->A0[j];
     x.p_signal = d->p_signal;
     x.gain_lin = d->gain_lin;
+    x.first_point = d->first_point;
 
     Yaman4Params p;
     memset(&p, 0, sizeof(p));
@@ -629,11 +898,26 @@ int yaman4_sweep_launch(const fpa_sweep_desc* d, cudaStream_t st) {
     p.n_saved    = fpa_n_saved(n_steps, d->save_every);
     p.coef       = make_coef(d->gamma / sc, d->alpha / sc, p.h);
 
-    const long blocks = (long)((B + kFastThreads - 1) / kFastThreads);
-    if (d->alpha == 0.0)
-        yaman4_sweep_kernel<false, kFastThreads, kSweepMinBlocks><<<blocks, kFastThreads, 0, st>>>(p, x);
-    else
-        yaman4_sweep_kernel<true, kFastThreads, kSweepMinBlocks><<<blocks, kFastThreads, 0, st>>>(p, x);
+    // ---- z-segment scheduler when the batch is a wave or more, else the whole-run kernel
+    const bool lossless = d->alpha == 0.0;
+    const int  ctas = lossless ? resident_ctas(yaman4_sweep_seg_kernel<false, kFastThreads, kSweepMinBlocks>, kFastThreads)
+                               : resident_ctas(yaman4_sweep_seg_kernel<true, kFastThreads, kSweepMinBlocks>, kFastThreads);
+    SegParams  g;
+    bool       use_seg = false;
+    rc = seg_plan(B, n_steps, ctas, kFastThreads, scratch, scratch_bytes, st, g, use_seg);
+    if (rc != FPA_OK) return rc;
+    if (use_seg) {
+        if (lossless)
+            yaman4_sweep_seg_kernel<false, kFastThreads, kSweepMinBlocks><<<ctas, kFastThreads, 0, st>>>(p, x, g);
+        else
+            yaman4_sweep_seg_kernel<true, kFastThreads, kSweepMinBlocks><<<ctas, kFastThreads, 0, st>>>(p, x, g);
+    } else {
+        const long blocks = (long)((B + kFastThreads - 1) / kFastThreads);
+        if (lossless)
+            yaman4_sweep_kernel<false, kFastThreads, kSweepMinBlocks><<<blocks, kFastThreads, 0, st>>>(p, x);
+        else
+            yaman4_sweep_kernel<true, kFastThreads, kSweepMinBlocks><<<blocks, kFastThreads, 0, st>>>(p, x);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "yaman4_sweep_kernel launch");
     return FPA_OK;

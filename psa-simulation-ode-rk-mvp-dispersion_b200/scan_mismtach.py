@@ -356,17 +356,27 @@ def rerun_point_with_trace(*, cfg: SimulationConfig, lambda_p1_m: float, lambda_
 
 def sweep_dbeta_gain(*, cfg: SimulationConfig, delta_beta, gamma: float, alpha: float, p_in,
                      phase_in=None, length_unit: str = "km", gain_mode: GainMode = "end",
-                     device: Optional[int] = None) -> dict:
+                     device: Optional[int] = None, devices=None) -> dict:
     """1-D phase-mismatch sweep with PROVIDED dbeta (BASELINE config 3): for each dbeta_k
     Gs = metric(P3)/(P3(0)+1e-30), Gi = metric(P4)/(p_in[2]+1e-30) with metric = end | max over
-    saved samples (scan_mismtach.py:139-156; the idler is normalised by the SIGNAL seed, :82-83)."""
+    saved samples (scan_mismtach.py:139-156; the idler is normalised by the SIGNAL seed, :82-83).
+    'end' is the LAST SAVED sample, Pz[-1] (scan_mismtach.py:33-34): when save_every does not divide
+    the step count that is not the end of the fiber, and the (rare) case is served from the trace.
+    `devices=[...]` splits the points over several GPUs of the box."""
     if gain_mode not in ("end", "max"):
         raise ValueError(f"Unknown gain_mode={gain_mode!r}. Use 'end' or 'max'.")
     p0 = np.asarray(list(p_in), dtype=float)
     A0 = make_initial_amplitudes(p0, phase_in)
+    s = _length_scale_to_m(length_unit)
+    n_steps = int(round(float(cfg.z_max) * s / (float(cfg.dz) * s)))
+    ragged = gain_mode == "end" and n_steps % int(cfg.save_every) != 0
     r = run_batch_simulation(cfg, gamma=gamma, alpha=alpha, delta_beta=delta_beta, A0=A0,
-                             length_unit=length_unit, outputs=("end", "pmax"), device=device)
-    P_metric = np.abs(r["A_end"]) ** 2 if gain_mode == "end" else r["Pmax"]
+                             length_unit=length_unit, outputs=("trace",) if ragged else ("end", "pmax"),
+                             device=device, devices=devices)
+    if ragged:
+        P_metric = np.abs(r["A_trace"][:, -1, :]) ** 2
+    else:
+        P_metric = np.abs(r["A_end"]) ** 2 if gain_mode == "end" else r["Pmax"]
     eps = 1e-30
     Ps0 = float(np.abs(A0[2]) ** 2)
     return {"Gs": P_metric[:, 2] / (Ps0 + eps), "Gi": P_metric[:, 3] / (float(p0[2]) + eps),

@@ -158,8 +158,9 @@ def run_single_simulation(cfg: SimulationConfig, *, gamma: float, alpha: float,
 
 def run_batch_simulation(cfg: SimulationConfig, *, gamma, alpha, delta_beta, p_in=None, phase_in=None,
                          A0=None, length_unit: str = "m", outputs: Sequence[str] = ("end", "pmax"),
-                         phase_exact: bool = False, device: Optional[int] = None) -> dict:
-    """B runs in one kernel launch.  `delta_beta` [B] (per length_unit); gamma / alpha scalars
+                         phase_exact: bool = False, device: Optional[int] = None, devices=None) -> dict:
+    """B runs in one kernel launch (`devices=[0, 1, ...]`: one launch per listed GPU, each on its own
+    contiguous share of the points, bit-identical results).  `delta_beta` [B] (per length_unit); gamma / alpha scalars
     or [B]; initial state from (p_in, phase_in) shared by all points, or explicit A0 [B,4] / [4].
     outputs: any of 'end' (A_end[B,4]), 'pmax' (max over SAVED samples of |A|^2, [B,4]),
     'trace' (A[B,n_saved,4] and z[n_saved]).  `status[B]` = first non-finite step or -1; with
@@ -176,7 +177,7 @@ def run_batch_simulation(cfg: SimulationConfig, *, gamma, alpha, delta_beta, p_i
     r = _device.yaman4_batch(db, np.asarray(gamma, dtype=float) / s, np.asarray(alpha, dtype=float) / s,
                              A0, z_max=z_max, n_steps=n_steps, save_every=cfg.save_every,
                              trace="trace" in want, end="end" in want, pmax="pmax" in want,
-                             check_nan=cfg.check_nan, phase_exact=phase_exact, device=device)
+                             check_nan=cfg.check_nan, phase_exact=phase_exact, device=device, devices=devices)
     if "trace" in want:
         grid = np.linspace(0.0, z_max, n_steps + 1)
         r["z"] = np.concatenate((grid[:1], grid[cfg.save_every::cfg.save_every])) / s

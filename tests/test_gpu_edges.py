@@ -139,7 +139,12 @@ def test_sweep_results_written_into_pinned_host_buffers(gpu, golden):
     lam3 = np.linspace(1400e-9, 1700e-9, 501)          # wide enough to hold invalid plans
     kw = dict(cfg=cfg, lambda_p1_m=lam1, lambda_signal_m=lam3, lambda_p2_m=1558e-9, gamma=11.5e-3, alpha=1e-4,
               p_in=golden["b4_p_in"], dispersion=disp, gain_unit="dB")
-    pageable = gpu.scan_mismtach.sweep_gain_2d(**kw)
+    plain = {k: np.full((37, 501), -9, dt) for k, dt in
+             (("gain_lin", np.float64), ("dbeta", np.float64), ("valid", np.int32), ("status", np.int32))}
+    pageable = gpu.scan_mismtach.sweep_gain_2d(out=plain, **kw)       # pageable memory: staged + copied
+    default = gpu.scan_mismtach.sweep_gain_2d(**kw)                   # library-owned page-locked pool
+    for k in ("gain", "gain_lin", "dbeta", "valid", "status"):
+        assert np.array_equal(default[k], pageable[k], equal_nan=True), k
     bufs = {k: gpu._lib.pinned_empty((37, 501), dt) for k, dt in
             (("gain_lin", np.float64), ("dbeta", np.float64), ("valid", np.int32), ("status", np.int32))}
     for v in bufs.values():

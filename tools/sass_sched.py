@@ -193,15 +193,25 @@ def branch_target(x):
     return int(m.group(1), 16) if m else None
 
 
-def hot_loop(ins):
-    """(lo, hi) addresses of the largest backward-branch span = the z-loop."""
-    best = (0, 0)
+def hot_loop(ins, min_fp64=24):
+    """(lo, hi) addresses of the z-loop: the backward-branch span with the most FP64 instructions among
+    the spans that hold no other FP64-carrying loop (>= min_fp64 FP64 instructions) inside them.  For a
+    kernel whose only big loop is the z-loop that is the largest backward span; in the persistent kernels
+    (a work-item loop around prologue + z-loop) it is still the z-loop, so the per-item prologue with its
+    unrolled double-double powers is never touched."""
+    spans = []
     for x in ins:
         if x.base == "BRA":
             tgt = branch_target(x)
-            if tgt is not None and tgt < x.addr and x.addr - tgt > best[1] - best[0]:
-                best = (tgt, x.addr)
-    return best
+            if tgt is not None and tgt < x.addr:
+                n = sum(1 for y in ins if y.is_fp64 and tgt <= y.addr <= x.addr)
+                spans.append((tgt, x.addr, n))
+    leaves = [s for s in spans if s[2] > 0 and not any(
+        o is not s and s[0] <= o[0] and o[1] <= s[1] and o[2] >= min_fp64 for o in spans)]
+    if not leaves:
+        return (0, 0)
+    lo, hi, _ = max(leaves, key=lambda s: (s[2], s[1] - s[0]))
+    return (lo, hi)
 
 
 def hot_blocks(ins, min_fp64=24):
