@@ -3,8 +3,9 @@
 The reference is pure Python: its "build" is CPython's compiler.  This recipe compiles the modules where
 they lie under /root/reference (read-only; nothing is copied) and writes ONLY the resulting .pyc files
 into oracle/_ref/ (git-ignored, not gpurun-ignored: like our own built .so files they travel to the GPU
-box, where /root/reference does not exist).  Sourceless imports of those .pyc files give the UNMODIFIED
-reference implementation on the GPU box's host cores:
+box, where /root/reference does not exist; they are named <module>.pycode because the snapshot drops
+*.pyc).  Loading those code objects gives the UNMODIFIED reference implementation on the GPU box's host
+cores:
 
     bench.py --impl reference      times it (cpu_baseline.kind = "reference")
     tests/test_oracle_cpu.py       re-checks oracle/fwm_oracle.py against it, bit for bit, wherever
@@ -33,7 +34,7 @@ def build(force: bool = False) -> bool:
         return available()
     OUT.mkdir(exist_ok=True)
     for name in MODULES:
-        src, dst = REF_SRC / f"{name}.py", OUT / f"{name}.pyc"
+        src, dst = REF_SRC / f"{name}.py", OUT / f"{name}.pycode"
         if force or not dst.exists() or dst.stat().st_mtime < src.stat().st_mtime:
             # unchecked pycs: the source path recorded inside does not exist on the GPU box
             py_compile.compile(str(src), cfile=str(dst), dfile=f"<reference>/{name}.py", doraise=True,
@@ -45,7 +46,7 @@ def build(force: bool = False) -> bool:
 def available() -> bool:
     tag = OUT / "PYTHON_VERSION"
     return (tag.exists() and tag.read_text().strip() == f"{sys.version_info[0]}.{sys.version_info[1]}" and
-            all((OUT / f"{m}.pyc").exists() for m in MODULES))
+            all((OUT / f"{m}.pycode").exists() for m in MODULES))
 
 
 class _Anything:
@@ -61,10 +62,32 @@ class _Anything:
         return iter((self, self))
 
 
+class _RefFinder:
+    """Meta-path finder that serves the reference's module names from oracle/_ref/<name>.pycode
+    (a .pyc by another name: 16-byte header + marshalled code object)."""
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.util
+
+        if name in MODULES and (OUT / f"{name}.pycode").exists():
+            return importlib.util.spec_from_loader(name, self, origin=str(OUT / f"{name}.pycode"))
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        import marshal
+
+        blob = (OUT / f"{module.__name__}.pycode").read_bytes()
+        module.__file__ = str(OUT / f"{module.__name__}.pycode")
+        exec(marshal.loads(blob[16:]), module.__dict__)
+
+
 def load() -> types.SimpleNamespace:
-    """Import the byte-compiled reference (sourceless) under private module names `_ref_<name>` would break
-    its own absolute imports, so the modules are imported under their own names from a path entry that is
-    removed again; callers hold on to the returned namespace."""
+    """Import the byte-compiled reference.  Its modules import each other by their plain names, so they are
+    imported under those names through a temporary finder and then taken out of sys.modules again (the
+    product package has same-named modules of its own); callers hold on to the returned namespace."""
     if not available():
         raise ImportError("oracle/_ref is not built (run oracle/build_ref.py where /root/reference exists)")
     import importlib
@@ -75,13 +98,14 @@ def load() -> types.SimpleNamespace:
         mpl.pyplot = plt
         sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
     saved = {m: sys.modules.pop(m) for m in MODULES if m in sys.modules}
-    sys.path.insert(0, str(OUT))
+    finder = _RefFinder()
+    sys.meta_path.insert(0, finder)
     try:
         mods = {m: importlib.import_module(m) for m in MODULES if m != "io_fwm"}
         for m in mods.values():
             assert str(OUT) in str(getattr(m, "__file__", "")), f"{m.__name__} did not come from oracle/_ref"
     finally:
-        sys.path.remove(str(OUT))
+        sys.meta_path.remove(finder)
         for m in MODULES:
             sys.modules.pop(m, None)
         sys.modules.update(saved)

@@ -699,8 +699,11 @@ constexpr int kSweepMinBlocks = 4;
 // z-segment scheduler: RK4 steps per segment (multiples of kResync), chosen by measurement
 // (profiles/r2_seg_tune.txt): 64 below two waves of the resident warps, 128 above -- with those the
 // scheduler is at least as fast as the whole-run kernel at every batch of one wave or more
-// (1.00 waves 68 -> 83 % of the FP64 peak, 1.65 waves 80.8 -> 86.2 %, 13.2 waves 87.2 -> 87.3 %).
-constexpr int kSegStepsShort = 64, kSegStepsLong = 128;
+// (1.00 waves 68 -> 83 % of the FP64 peak, 1.65 waves 80.8 -> 86.2 %, 6.6 waves 85.4 -> 87.2 %,
+// 13.2 waves 87.2 -> 87.3 %).  Above kSegMaxWaves waves the whole-run kernel is kept: its tail is down
+// to ~1 % there, and the state hand-over of a batch that large no longer fits the 126 MB L2 (1e6 points:
+// 116 MB per hand-over, 3.9 GB of DRAM traffic per sweep against 0.1 MB for the whole-run kernel).
+constexpr int kSegStepsShort = 64, kSegStepsLong = 128, kSegMaxWaves = 8;
 
 // ---- z-segment scheduler: scratch layout and launch geometry
 static size_t seg_align(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -730,7 +733,8 @@ static int resident_ctas(Kernel kernel, int threads) {
 // Decides whether a batch runs through the scheduler and, if so, fills `g` and clears its counters.
 // Legal when the caller gave enough scratch, every segment holds at least one item per resident warp
 // (then an item's predecessor is finished when it is handed out) and the run has at least two segments.
-// FPA_SWEEP_SEG=0 forces the whole-run kernels, FPA_SWEEP_SEG_STEPS overrides the segment length (tools, tests).
+// FPA_SWEEP_SEG=0 forces the whole-run kernels, =2 lifts the kSegMaxWaves cap, FPA_SWEEP_SEG_STEPS overrides the
+// segment length (tools, tests).
 static int seg_plan(int64_t B, int64_t n_steps, int ctas, int threads, void* scratch, int64_t scratch_bytes,
                     cudaStream_t st, SegParams& g, bool& use_seg) {
     const int64_t n_warps = (B + 31) / 32, resident_warps = (int64_t)ctas * (threads / 32);
@@ -738,7 +742,8 @@ static int seg_plan(int64_t B, int64_t n_steps, int ctas, int threads, void* scr
     seg_steps = (seg_steps + kResync - 1) / kResync * kResync;
     if (seg_steps < kResync) seg_steps = kResync;
     use_seg = env_int("FPA_SWEEP_SEG", 1) != 0 && scratch != nullptr && scratch_bytes >= yaman4_scratch_bytes(B) &&
-              n_warps >= resident_warps && n_steps >= 2 * (int64_t)seg_steps &&
+              n_warps >= resident_warps && (n_warps < kSegMaxWaves * resident_warps || env_int("FPA_SWEEP_SEG", 1) == 2) &&
+              n_steps >= 2 * (int64_t)seg_steps &&
               n_warps * ((n_steps + seg_steps - 1) / seg_steps) < 4000000000LL;
     if (!use_seg) return FPA_OK;
     char* base = static_cast<char*>(scratch);

@@ -211,3 +211,44 @@ def test_fast_kernel_algorithm_model_vs_oracle(oracle):
     S = M.integrate(A0, 0.01, 0.0, -0.013, 500.0, 500, save_every=100)
     assert len(S) == len(A)
     assert np.max(np.abs(np.array(S) - A)) / np.max(np.abs(A)) < 1e-13
+
+
+# ------------------------------------------------------------------ oracle vs the byte-compiled reference
+def test_oracle_is_bit_equal_to_the_compiled_reference(oracle):
+    """oracle/_ref holds the reference's own modules, byte-compiled by oracle/build_ref.py where
+    /root/reference exists; it travels to the GPU box.  Wherever it is present the oracle port is re-pinned
+    against it: sweep metric, Delta-beta (all methods) and a full trace, bit for bit."""
+    from oracle import build_ref
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not built here (no /root/reference)")
+    R = build_ref.load()
+    lam1, lam2 = 1550e-9, 1558e-9
+    lam3 = np.linspace(700e-9, 1600e-9, 7)                     # the first one has no positive idler: NaN
+    om = oracle.plan_from_wavelengths(lam1, lam2, 1554e-9)
+    oc, _, _ = oracle.symmetric_vars(om)
+    od = oracle.taylor_from_D_S(oracle.TWO_PI * oracle.C_LIGHT / oc, 0.1, 0.02, 0.0, omega_ref=oc)
+    rd = R.dispersion.DispersionParams(omega_ref=od.omega_ref, beta2=od.b[2], beta3=od.b[3], beta4=od.b[4])
+    alpha = float(np.log(10) / 10 * 0.5 / 1000)
+    p_in = [0.1, 0.1, 1e-7, 1e-7]
+    for unit, s in (("m", 1.0), ("km", 1e-3)):
+        cfg = R.config.custom_simulation_config(z_max=40.0 * s, dz=0.2 * s, save_every=10)
+        rdu = R.dispersion.DispersionParams(omega_ref=od.omega_ref, beta2=od.b[2] / s, beta3=od.b[3] / s, beta4=od.b[4] / s)
+        for method, ometh in (("symmetric_even", oracle.SYMMETRIC_EVEN), ("general_taylor", oracle.GENERAL_TAYLOR)):
+            pm = R.phase_matching.PhaseMatchingConfig(method=method)
+            _, g_ref, db_ref = R.scan_mismtach.plot_max_gain_and_dbeta_vs_lambda_signal(
+                cfg=cfg, lambda_p1_m=lam1, lambda_p2_m=lam2, lambda_signal_m=lam3, gamma=11.5e-3 / s, alpha=alpha / s,
+                p_in=p_in, dispersion=rdu, phase_matching_cfg=pm, length_unit=unit, gain_unit="dB",
+                show_progress=False, show=False)
+            g, db = oracle.sweep_lambda3_gain(
+                lam1=lam1, lam2=lam2, lam3_arr=lam3, z_max=40.0 * s, dz=0.2 * s, save_every=10, check_nan=True,
+                gamma=11.5e-3 / s, alpha=alpha / s, p_in=p_in,
+                disp=oracle.Taylor(od.omega_ref, 0.0, 0.0, od.b[2] / s, od.b[3] / s, od.b[4] / s), method=ometh,
+                length_unit=unit, gain_unit="dB")
+            assert np.isnan(g_ref[0]) and np.isfinite(g_ref[1:]).all()
+            assert np.array_equal(g, g_ref, equal_nan=True) and np.array_equal(db, db_ref, equal_nan=True)
+    z_ref, A_ref = R.simulation.run_single_simulation(
+        R.config.custom_simulation_config(z_max=100.0, dz=0.1, save_every=10), gamma=11.5e-3, alpha=alpha, omega=om,
+        p_in=[0.5, 0.5, 1e-5, 1e-5], dispersion=rd)
+    z, A, _ = oracle.single_run(z_max=100.0, dz=0.1, save_every=10, check_nan=True, gamma=11.5e-3, alpha=alpha,
+                                omega=om, p_in=[0.5, 0.5, 1e-5, 1e-5], disp=od)
+    assert np.array_equal(z, z_ref) and np.array_equal(A, A_ref)

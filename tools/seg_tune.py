@@ -90,7 +90,7 @@ for n1 in rows:
     tf0 = 568.0 * B * n_steps / (ms0 * 1e-3) / 1e12
     line = f"n1={n1:5d} points={B:8d} waves={waves:5.2f} | whole-run {ms0:8.3f} ms {tf0:6.2f} TF ({100 * tf0 / peak_tf:4.1f}%)"
     for ss in seg_list:
-        ms, g, s, dd = run(n1, {"FPA_SWEEP_SEG": "1", "FPA_SWEEP_SEG_STEPS": str(ss)})
+        ms, g, s, dd = run(n1, {"FPA_SWEEP_SEG": "2", "FPA_SWEEP_SEG_STEPS": str(ss)})
         same = g.tobytes() == g0.tobytes() and s.tobytes() == s0.tobytes() and dd.tobytes() == d0.tobytes()
         tf = 568.0 * B * n_steps / (ms * 1e-3) / 1e12
         line += f" | seg{ss:<3d} {ms:8.3f} ms ({100 * tf / peak_tf:4.1f}%){'' if same else ' DIFFERENT!'}"

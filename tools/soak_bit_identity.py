@@ -25,7 +25,7 @@ repeats = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 od = Bn.fiber_dispersion(O)
 disp = fpa.dispersion.DispersionParams(omega_ref=od.omega_ref, beta2=od.b[2], beta3=od.b[3], beta4=od.b[4])
 cfg = fpa.config.custom_simulation_config(z_max=Bn.Z_MAX, dz=Bn.DZ, save_every=Bn.SAVE_EVERY)
-lam1, lam3 = Bn.workload_axes(0, 1, "weak")
+lam1, lam3 = Bn.grid_axes()
 
 
 def digest(alpha):
