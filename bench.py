@@ -78,11 +78,12 @@ def fiber_dispersion(O):
     return O.taylor_from_D_S(O.TWO_PI * O.C_LIGHT / oc, 0.1, 0.02, 0.0, omega_ref=oc)
 
 
-def ncu_traffic_bytes():
-    """dram read + write bytes per launch of the sweep kernel from the newest committed ncu summary
-    (profiles/*_ncu_yaman4_sweep*.csv); (None, None) when there is none."""
+def ncu_traffic_bytes(seg: bool):
+    """dram read + write bytes per launch of the sweep kernel that ran -- the whole-run kernel or the
+    z-segment scheduler -- from the newest committed ncu summary of that kernel
+    (profiles/r*_ncu_yaman4_sweep_kernel*.csv / r*_ncu_yaman4_sweep_seg_kernel*.csv); (None, None) when there is none."""
     best = None
-    for path in sorted((ROOT / "profiles").glob("r*_ncu_yaman4_sweep*.csv")):
+    for path in sorted((ROOT / "profiles").glob(f"r*_ncu_yaman4_sweep_{'seg_' if seg else ''}kernel*.csv")):
         vals = {}
         for line in path.read_text().splitlines():
             parts = line.split(",")
@@ -349,7 +350,7 @@ def run_ours(args) -> None:
     # child of a CUDA process is fragile even when it never touches the GPU).  The sample is compared
     # with the GPU results further down.
     cpu_leg = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.shard_of <= 1:
         kind = cpu_kind()
         cores = os.cpu_count() or 1
         n_pts = max(64, (40 if kind == "port" else 14) * cores)      # ~10-20 s of wall time on the box's cores
@@ -380,6 +381,8 @@ def run_ours(args) -> None:
     # ---- headline: the fixed 1e6-point grid, split into `world` contiguous point ranges (strong scaling)
     total_points = N1 * N3
     lo, hi = balanced_range(total_points, world, rank)
+    if args.shard_of > 1:       # profiling aid: rank 0's share of an N-way split, on this one GPU
+        lo, hi = balanced_range(total_points, args.shard_of, 0)
     sweep = DeviceSweep(fpa, torch, dev, N1, lo, hi - lo, disp, pm_cfg)
     B = hi - lo
     even = total_points % world == 0
@@ -398,7 +401,7 @@ def run_ours(args) -> None:
 
     ms_total, k_ms, window, parts = timed_sweeps(torch, dist, sweep, gather_strong, world, args.steps, args.warmup, t_flush, dev)
     clocks = sampler.summary(*window) if rank == 0 else None
-    value = total_points * n_steps * args.steps / (ms_total * 1e-3)
+    value = (hi - lo if args.shard_of > 1 else total_points) * n_steps * args.steps / (ms_total * 1e-3)
     kernel_ms = float(np.mean(k_ms))
     achieved_tf = FLOPS_PER_POINT_STEP * B * n_steps / (kernel_ms * 1e-3) / 1e12
     gain_dev = sweep.t_gain.cpu().numpy()
@@ -451,7 +454,9 @@ def run_ours(args) -> None:
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_variants = {}
-    if world == 1:
+    if args.shard_of > 1:
+        e2e_value, e2e_api, h2d, d2h = None, "not measured with --shard-of", 0, 0
+    elif world == 1:
         sec_a, res = time_calls(lambda: public_call(lam1), e2e_steps)
         e2e_value = total_points * n_steps * e2e_steps / sec_a
         assert res["gain_lin"].tobytes() == full_dev.reshape(N1, N3).tobytes(), "e2e and device-resident sweeps differ"
@@ -524,7 +529,7 @@ def run_ours(args) -> None:
 
     # ---- secondary configurations (N = 1)
     secondary, sec_window = None, None
-    if world == 1 and not args.no_secondary:
+    if world == 1 and not args.no_secondary and args.shard_of <= 1:
         peak_tf, _ = fpa._device.fp64_peak(iters=2048, device=local)
         t_a = time.time()
         secondary = run_secondary(fpa, torch, dev, local, disp, peak_tf, t_flush)
@@ -541,13 +546,14 @@ def run_ours(args) -> None:
     name = C.create_string_buffer(128)
     lib.fpa_device_info(local, C.byref(sm_count), C.byref(khz), name, 128)
     nominal_tf = sm_count.value * 64 * 2 * khz.value * 1e3 / 1e12
-    traffic, traffic_src = ncu_traffic_bytes()
     seg_on = os.environ.get("FPA_SWEEP_SEG", "1") != "0" and 148 * 16 <= (B + 31) // 32 < 8 * 148 * 16
+    traffic, traffic_src = ncu_traffic_bytes(seg_on)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "points_total": total_points, "points_per_gpu": B, "rk4_steps": n_steps,
+        "config": {"workload": WORKLOAD + (f" -- ONLY the first of {args.shard_of} shards (profiling aid)" if args.shard_of > 1 else ""),
+                   "points_total": total_points, "points_per_gpu": B, "rk4_steps": n_steps,
                    "parallelism": f"flattened point range split x{world}, final all-gather of the gain map" if world > 1 else "one GPU",
                    "l2": f"{FLUSH_BYTES >> 20} MiB buffer written between steps (inside the timed region); "
                          "the kernel keeps its state in registers"},
@@ -782,6 +788,8 @@ def main() -> None:
                          "'both' (default) and 'weak' also time 1e6 points per GPU and report it under \"weak\"")
     ap.add_argument("--no-cpu-baseline", action="store_true",
                     help="skip the CPU leg (profiling runs under ncu)")
+    ap.add_argument("--shard-of", type=int, default=1,
+                    help="profiling aid (one GPU): run only rank 0's share of an N-way split of the grid, e.g. 8 -> 125 000 points")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the secondary configurations (profiling runs under ncu)")
     args = ap.parse_args()

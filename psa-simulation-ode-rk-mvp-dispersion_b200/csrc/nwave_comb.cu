@@ -29,6 +29,7 @@
 #include "fpa_common.cuh"
 
 #include <assert.h>
+#include <stdlib.h>
 
 // compute-sanitizer is not available on the B200 pool: -DFPA_BOUNDS_CHECK turns every shared-memory
 // sequence access of this file into a checked one (device assert), tools/bounds_check.py builds that
@@ -84,7 +85,7 @@ struct CombSmem {
     double2 *y, *ys, *yn, *E, *Eh, *rot;  // [N] state, stage state, accumulator, phases
     double2 *At;                          // [seq_words]  At on the grid at padx(slot), zeros above M
     double2 *Y;                           // [seq_words]  Y[padx(q)] = X_{M-1-q}, zeros above 2M-2
-    double2 *R;                           // [M + kPad]
+    double2 *R;                           // [comb_r_words(M)]
     double*  beta;
     int*     slot;
 };
@@ -96,8 +97,10 @@ __host__ __device__ inline int comb_seq_words(int M, int sk) {
     return e + (e >> sk) + 1;
 }
 
+__host__ __device__ inline int comb_r_words(int M) { return M + (M >> 3) + kPad; }  // room for the padx<3> layout
+
 __host__ __device__ inline size_t comb_point_doubles(int N, int M, int sk) {
-    const size_t d = 2 * (size_t)(6 * N + 2 * comb_seq_words(M, sk) + (M + kPad)) + (size_t)N + (size_t)(N + 1) / 2 + 2;
+    const size_t d = 2 * (size_t)(6 * N + 2 * comb_seq_words(M, sk) + comb_r_words(M)) + (size_t)N + (size_t)(N + 1) / 2 + 2;
     return (d + 1) & ~(size_t)1;  // keeps every point's block 16-byte aligned
 }
 
@@ -112,7 +115,7 @@ __device__ __forceinline__ CombSmem comb_carve(double* base, int N, int M, int s
     s.At   = s.rot + N;
     s.Y    = s.At + comb_seq_words(M, sk);
     s.R    = s.Y + comb_seq_words(M, sk);
-    s.beta = reinterpret_cast<double*>(s.R + (M + kPad));
+    s.beta = reinterpret_cast<double*>(s.R + comb_r_words(M));
     s.slot = reinterpret_cast<int*>(s.beta + N);
     return s;
 }
@@ -418,6 +421,476 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
 #undef WS_LD
 #undef WS_ST
 
+// =====================================================================================================
+// Warp-per-point kernel for batches (nwave_comb8_kernel): tiles of EIGHT outputs with a rolling window.
+//
+// The tiles-of-4 mapping above is bound by shared-memory wavefronts, not by the FP64 pipe (ncu, round 1:
+// LSU 79 % busy at 63 % FP64 activity): a block of 8 terms loads 19 words for 128 FMAs.  Here a lane owns 8
+// adjacent outputs and walks its part of the term range one term at a time: the 8-word window of w slides
+// by one word per term, so a term costs ONE new word of w and one (broadcast) word of a for 32 FMAs --
+// 40 loads per 512 FMAs.  The loads of term k+1 are issued before the FMAs of term k (software pipeline);
+// the window lives in registers and rotates by renaming (the 8-term body is fully unrolled).
+// Sequences are stored with one spare word after every 8 (padx<3>): the eight lanes of a quarter-warp hold
+// neighbouring tiles, 9 words apart, i.e. in eight different 16-byte bank groups -- conflict-free.
+// Lane layout: LP = 2^lp lanes hold the tiles of one part of the term range (LP >= number of tiles), the
+// 32 / LP parts are summed by xor-shuffles.  For M = 64: 8 tiles x 4 parts.
+// =====================================================================================================
+constexpr int kSk8 = 3;
+
+// re + i*im += a * w
+__device__ __forceinline__ void cmac(double& re, double& im, const double2 a, const double2 w) {
+    re = fma(a.x, w.x, fma(-a.y, w.y, re));
+    im = fma(a.x, w.y, fma(a.y, w.x, im));
+}
+
+// (a.x, +-a.y): conj(a) * w is computed as a' * w with the sign bit of a.y flipped after the load (an integer
+// operation on the high word: the FP64 pipe does not see it), so ONE instance of the loop below serves the
+// auto-correlation (conj) and the convolution -- the unrolled body is 4.4 KB of code, and three inlined copies
+// of it plus the four warps of a sub-partition at different places thrashed the instruction cache
+// (stall_no_instruction 0.72 per issue in the first version of this kernel).
+__device__ __forceinline__ double2 load_a(const double2* p, int sign_flip) {
+    double2 v = *p;
+    v.y = __hiloint2double(__double2hiint(v.y) ^ sign_flip, __double2loint(v.y));
+    return v;
+}
+
+// acc[t] += a'[i] * w[obase + i + t] for i in [i0, i1), t in [0, 8).  obase and i0 are multiples of 8 and
+// i1 - i0 is a multiple of 8.  Reads up to w[obase + i1 + 7] and a[i1].
+__device__ __forceinline__ void roll8_mac(const double2* __restrict__ a, const double2* __restrict__ w, int obase,
+                                          int i0, int i1, int sign_flip, double (&re)[8], double (&im)[8]) {
+    double2        win[8];
+    const double2* wp = w + padx<kSk8>(obase + i0);
+    const double2* ap = a + padx<kSk8>(i0);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) win[t] = wp[t];
+    double2 av = load_a(ap, sign_flip);
+    for (int i = i0; i < i1; i += 8) {
+        wp += 9;  // the next 8 words of w (one spare word in between)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            // operands of the next term are requested before this term's 32 FMAs
+            const double2 nw = wp[k];
+            const double2 an = load_a(ap + (k < 7 ? k + 1 : 9), sign_flip);   // k == 7: first word of the next group
+#pragma unroll
+            for (int t = 0; t < 8; ++t) cmac(re[t], im[t], av, win[(k + t) & 7]);
+            win[k] = nw;
+            av = an;
+        }
+        ap += 9;
+    }
+}
+
+// The same for exactly FOUR terms starting at i0 (a multiple of 4): the short parts of small plans.
+__device__ __forceinline__ void roll4_mac(const double2* __restrict__ a, const double2* __restrict__ w, int obase,
+                                          int i0, int sign_flip, double (&re)[8], double (&im)[8]) {
+    double2 win[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) win[t] = w[padx<kSk8>(obase + i0 + t)];
+    const double2* ap = a + padx<kSk8>(i0);                  // 4 words, no pad inside (i0 % 4 == 0)
+    const double2* wp = w + padx<kSk8>(obase + i0 + 8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double2 av = load_a(ap + k, sign_flip);
+        double2       nw = make_double2(0.0, 0.0);
+        if (k < 3) nw = wp[k];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) cmac(re[t], im[t], av, win[(k + t) & 7]);
+        win[k] = nw;
+    }
+}
+
+// One level of the reduce-scatter over the parts: lanes d apart exchange HALF of the CNT values they hold
+// and keep the sum of the other half (the lane whose bit d is set keeps the upper half).  Against a
+// butterfly all-reduce this moves 8+4+2 instead of 16+16+16 doubles for three levels, and leaves the outputs
+// of a tile spread over the parts, so that all of them store.
+template <int CNT>
+__device__ __forceinline__ void scatter_level(double (&re)[8], double (&im)[8], int d, bool up) {
+    if (CNT > 1) {
+        constexpr int H = CNT / 2 > 0 ? CNT / 2 : 1;
+#pragma unroll
+        for (int t = 0; t < H; ++t) {
+            const double sr = up ? re[t] : re[t + H], si = up ? im[t] : im[t + H];
+            const double kr = up ? re[t + H] : re[t], ki = up ? im[t + H] : im[t];
+            re[t] = kr + __shfl_xor_sync(0xffffffffu, sr, d);
+            im[t] = ki + __shfl_xor_sync(0xffffffffu, si, d);
+        }
+    } else {  // one value left: plain all-reduce (only the lane with all upper part bits clear stores)
+        re[0] += __shfl_xor_sync(0xffffffffu, re[0], d);
+        im[0] += __shfl_xor_sync(0xffffffffu, im[0], d);
+    }
+}
+
+// What a lane does in every correlation of the run -- both sums of a stage have the same shape (M outputs,
+// M terms), so this is computed ONCE per kernel: LP = 2^lp lanes hold the tiles of one part of the term range
+// (LP >= number of tiles, or all L lanes and several rounds of tiles), the L / LP parts are combined by the
+// reduce-scatter, after which the lane owns outputs [off, off + cnt) of its tile.
+struct Corr8Lane {
+    int lp, parts_log;   // log2 of lanes per part and of the number of parts
+    int tl, part;        // tile within a round, part
+    int i0, i1, half;    // term range of the part (half: exactly four terms)
+    int off, cnt;        // outputs of the tile this lane ends up with
+    int rounds, n_tiles, n_out, idle;
+};
+
+template <int L>
+__device__ __forceinline__ Corr8Lane corr8_lane(int n_terms, int n_out, int gl) {
+    Corr8Lane c;
+    c.n_out = n_out;
+    c.n_tiles = (n_out + 7) >> 3;
+    c.lp = 0;
+    while ((1 << c.lp) < c.n_tiles && (1 << c.lp) < L) ++c.lp;
+    int parts = L >> c.lp;
+    c.parts_log = 0;
+    while ((1 << c.parts_log) < parts) ++c.parts_log;
+    int chunk = (n_terms + parts - 1) / parts;
+    c.half = chunk <= 4;
+    chunk = c.half ? 4 : (chunk + 7) & ~7;
+    c.tl = gl & ((1 << c.lp) - 1);
+    c.part = gl >> c.lp;
+    c.i0 = c.part * chunk;
+    c.i1 = c.i0 + chunk;
+    const int end8 = (n_terms + 7) & ~7;
+    if (c.i1 > end8) c.i1 = end8;
+    c.idle = c.i0 >= n_terms;
+    c.rounds = (c.n_tiles + (1 << c.lp) - 1) >> c.lp;
+    c.off = ((c.part & 1) && c.parts_log >= 1 ? 4 : 0) + ((c.part & 2) && c.parts_log >= 2 ? 2 : 0) +
+            ((c.part & 4) && c.parts_log >= 3 ? 1 : 0);
+    c.cnt = 8 >> (c.parts_log < 3 ? c.parts_log : 3);
+    if (c.part >> 3) c.cnt = 0;            // more than 8 parts: the upper ones hold copies
+    return c;
+}
+
+// out[o] = sum_{i < n_terms} a'[i] * w[i + o] for o in [0, n_out), on the L lanes of one point.  The lane
+// that ends up with output o writes it: TO_R -> dst[padx(M-1-o)] (the convolution result R, o = M-1-n);
+// else -> Yc[padx(M-1-o)] = X_o and Yc[padx(M-1+o)] = conj(X_o) (the mirrored auto-correlation).
+// Stores are branch-free: a lane without a valid output writes to `trash` (a spare word nobody reads).
+#ifdef FPA_COMB_TIMING
+__device__ long long g_corr_ticks[8];
+#define FPA_CTICK(k)                                                           \
+    do {                                                                       \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                             \
+            const long long now_ = clock64();                                  \
+            g_corr_ticks[k] += now_ - ct_prev;                                 \
+            ct_prev = now_;                                                    \
+        }                                                                      \
+    } while (0)
+#define FPA_TICK8(k)                                  \
+    do {                                              \
+        if (b == 0 && gl == 0) {                      \
+            const long long now_ = clock64();         \
+            tk8[k] += now_ - t_prev8;                 \
+            t_prev8 = now_;                           \
+        }                                             \
+    } while (0)
+#else
+#define FPA_CTICK(k) ((void)0)
+#define FPA_TICK8(k) ((void)0)
+#endif
+
+// out[o] = sum_{i < n_terms} a'[i] * w[i + o] for o in [0, n_out), on the L lanes of one point.  The lane
+// that ends up with output o writes it: TO_R -> dst[padx(M-1-o)] (the convolution result R, o = M-1-n);
+// else -> dst[padx(M-1-o)] = X_o and dst[padx(M-1+o)] = conj(X_o) (the mirrored auto-correlation).
+// PLOG = log2 of the number of parts when it is known at compile time (the usual plan sizes), -1 = taken
+// from c.parts_log: with PLOG >= 0 the reduce-scatter and the stores are straight-line code.  Stores are
+// branch-free: a lane without a valid output writes to `trash` (a spare word nobody reads).
+template <int L, int PLOG, bool TO_R>
+__device__ __forceinline__ void corr8(const double2* a, const double2* w, const Corr8Lane& c, int sign_flip, int M,
+                                      double2* dst, double2* trash) {
+    const int LP = 1 << c.lp;
+    const int plog = PLOG >= 0 ? PLOG : c.parts_log;
+#ifdef FPA_COMB_TIMING
+    long long ct_prev = clock64();
+#endif
+    for (int r = 0; r < c.rounds; ++r) {
+        const int  tile = r * LP + c.tl;
+        const bool live = tile < c.n_tiles && !c.idle;
+        double     re[8], im[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) re[t] = im[t] = 0.0;
+        FPA_CTICK(0);
+        if (live) {
+            if (c.half)
+                roll4_mac(a, w, tile * 8, c.i0, sign_flip, re, im);
+            else
+                roll8_mac(a, w, tile * 8, c.i0, c.i1, sign_flip, re, im);
+        }
+        FPA_CTICK(1);
+        // reduce-scatter over the parts (the level count is uniform over the warp: shuffles stay convergent)
+        if (plog >= 1) scatter_level<8>(re, im, LP, (c.part & 1) != 0);
+        if (plog >= 2) scatter_level<4>(re, im, 2 * LP, (c.part & 2) != 0);
+        if (plog >= 3) scatter_level<2>(re, im, 4 * LP, (c.part & 4) != 0);
+        if (plog >= 4) scatter_level<1>(re, im, 8 * LP, false);
+        if (plog >= 5) scatter_level<1>(re, im, 16 * LP, false);
+        FPA_CTICK(2);
+        const int o0 = tile * 8 + c.off;
+        constexpr int kMaxOut = PLOG < 0 ? 8 : (8 >> (PLOG < 3 ? PLOG : 3));
+#pragma unroll
+        for (int t = 0; t < kMaxOut; ++t) {
+            const bool ok = t < c.cnt && o0 + t < c.n_out;
+            double2* q1 = ok ? dst + padx<kSk8>(M - 1 - (o0 + t)) : trash;
+            *q1 = make_double2(re[t], im[t]);
+            if (!TO_R) {
+                double2* q2 = ok ? dst + padx<kSk8>(M - 1 + (o0 + t)) : trash;
+                *q2 = make_double2(re[t], -im[t]);
+            }
+        }
+        FPA_CTICK(3);
+    }
+}
+
+// After the convolution of stage S: k_n = -(alpha/2) x + i*gamma*conj(E_n) R_n, the RK4 bookkeeping of that
+// stage AND the phase / rotated state of the NEXT stage (or of stage 0 of the next step) for one wave, in
+// one pass: the wave's state makes one shared-memory round trip per stage.  E holds exp(i*beta*z) at the
+// start of the step (from S = 2 on: at its end), Eh the phase the current stage's conj(E) uses.
+struct CombStep {
+    double gamma, nha, hh, h, h6, h3;
+};
+
+template <int S>
+__device__ __forceinline__ void wave_pass(const CombSmem& s, int j, int slot_pad, const CombStep& k, bool resync_next,
+                                          double z_next, bool check, int& nf) {
+    const double2 r = s.R[slot_pad];
+    const double2 e = S == 0 ? s.E[j] : s.Eh[j];
+    const double2 x = s.ys[j];
+    const double  fr = fma(r.y, e.y, r.x * e.x);
+    const double  fi = fma(r.y, e.x, -(r.x * e.y));
+    const double  kr = fma(k.nha, x.x, -(k.gamma * fi));
+    const double  ki = fma(k.nha, x.y, k.gamma * fr);
+    const double  wa = (S == 0 || S == 3) ? k.h6 : k.h3;
+    const double2 acc = s.yn[j];
+    double2       ysn, en;
+    if (S == 3) {
+        ysn = make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y));    // the step's result
+        s.y[j] = ysn;
+        s.yn[j] = ysn;
+        if (check && (nonfinite(ysn.x) || nonfinite(ysn.y))) nf = 1;
+        if (resync_next) {   // exact phase every kCombResync steps
+            double sn, cs;
+            sincos(s.beta[j] * z_next, &sn, &cs);
+            en = make_double2(cs, sn);
+        } else {
+            en = e;          // stage 3 ran at z + h: that is the next step's starting phase
+        }
+        s.E[j] = en;
+    } else {
+        const double  wb = S == 2 ? k.h : k.hh;
+        const double2 y0 = s.y[j];
+        s.yn[j] = make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y));
+        ysn = make_double2(fma(wb, kr, y0.x), fma(wb, ki, y0.y));
+        if (S == 1) {
+            en = e;          // stages 1 and 2 share the abscissa z + h/2
+        } else {             // S = 0 -> z + h/2 ; S = 2 -> z + h
+            const double2 rot = s.rot[j];
+            en = make_double2(fma(-e.y, rot.y, e.x * rot.x), fma(e.x, rot.y, e.y * rot.x));
+            s.Eh[j] = en;
+            if (S == 2) s.E[j] = en;
+        }
+    }
+    s.ys[j] = ysn;
+    s.At[slot_pad] = make_double2(fma(-ysn.y, en.y, ysn.x * en.x), fma(ysn.x, en.y, ysn.y * en.x));
+}
+
+// L lanes per scan point, 32 / L points per warp (all of them in lock-step: N, M and the step count are the
+// same for the whole batch).  L = 32 for batches that would otherwise leave sub-partitions without a warp;
+// L = 16 halves the shared-memory and shuffle operations per FMA (each lane runs twice as many terms per
+// window and per reduction) and is used once the batch still gives every sub-partition its warps.
+template <int L, int PLOG>
+__global__ void __launch_bounds__(kCombThreads, L == 32 ? 2 : 1) nwave_comb8_kernel(const CombParams p) {
+    extern __shared__ __align__(16) double comb_smem_raw[];
+    constexpr int PPW = 32 / L;              // points per warp
+    constexpr int kOwn = 128 / L;            // waves a lane owns at most (N <= 128)
+    const int     N = p.n_waves, M = p.span;
+    const int     lane = threadIdx.x & 31, gl = lane & (L - 1), grp = lane / L;
+    const int     sub = (threadIdx.x >> 5) * PPW + grp;                   // point slot inside the CTA
+    const int64_t b_raw = ((int64_t)blockIdx.x * (blockDim.x >> 5)) * PPW + sub;
+    if (((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PPW >= p.n_points) return;  // whole warps leave
+    // groups of a partly filled last warp run a copy of the last point (lock-step shuffles) and store nothing
+    const bool    real = b_raw < p.n_points;
+    const int64_t b = real ? b_raw : p.n_points - 1;
+    CombSmem s = comb_carve(comb_smem_raw + (size_t)sub * comb_point_doubles(N, M, kSk8), N, M, kSk8);
+    const unsigned gmask = L == 32 ? 0xffffffffu : (((1u << L) - 1u) << (grp * L));
+
+    const int    n_steps = p.n_steps;
+    const double z0 = p.z0;
+    const double h = (p.z_max - z0) / (double)n_steps;
+    CombStep     ks;
+    ks.gamma = p.gamma[b * p.gamma_stride];
+    ks.nha   = -0.5 * p.alpha[b * p.alpha_stride];
+    ks.h     = h;
+    ks.hh    = 0.5 * h;
+    ks.h6    = h / 6.0;
+    ks.h3    = ks.h6 + ks.h6;
+
+    const int words = comb_seq_words(M, kSk8);
+    for (int m = gl; m < words; m += L) {
+        s.At[m] = make_double2(0.0, 0.0);  // empty grid slots and the padding stay 0
+        s.Y[m]  = make_double2(0.0, 0.0);
+    }
+    for (int m = gl; m < comb_r_words(M); m += L) s.R[m] = make_double2(0.0, 0.0);
+    __syncwarp();
+    // per-wave state; stage 0 of the first step: exact phase at z0, ys = yn = y, At = y * E
+    for (int j = gl; j < N; j += L) {
+        const double bj = p.beta[b * p.beta_stride * N + j];
+        s.beta[j] = bj;
+        const double2 v = (reinterpret_cast<const double2*>(p.A0) + b * p.A0_stride * N)[j];
+        s.y[j] = s.ys[j] = s.yn[j] = v;
+        double sn, cs;
+        sincos(bj * ks.hh, &sn, &cs);
+        s.rot[j] = make_double2(cs, sn);
+        sincos(bj * z0, &sn, &cs);
+        s.E[j] = s.Eh[j] = make_double2(cs, sn);
+        s.At[padx<kSk8>(p.slot[j])] = make_double2(fma(-v.y, sn, v.x * cs), fma(v.x, sn, v.y * cs));
+    }
+
+    double2* tr = (p.A_trace && real) ? reinterpret_cast<double2*>(p.A_trace) + b * p.n_saved * N : nullptr;
+    if (tr) {
+        for (int j = gl; j < N; j += L) tr[j] = s.y[j];
+        tr += N;
+    }
+    double pm[kOwn];
+#pragma unroll
+    for (int q = 0; q < kOwn; ++q) {
+        const int j = gl + q * L;
+        pm[q] = (p.Pmax && j < N) ? fma(s.y[j].y, s.y[j].y, s.y[j].x * s.y[j].x) : 0.0;
+    }
+    int      save_ctr = p.save_every;
+    int32_t  bad = FPA_POINT_OK;
+    int      nf = 0;                                    // a component of the state entering the step is not finite
+    if (p.check)
+        for (int j = gl; j < N; j += L) nf |= (nonfinite(s.y[j].x) || nonfinite(s.y[j].y)) ? 1 : 0;
+    double2* const Yc = s.Y;                            // Yc[padx(q)] = X_{M-1-q}, q in [0, 2M-2]
+    double2* const trash = s.R + comb_r_words(M) - 1;   // spare word: target of the stores of lanes without an output
+    // padded positions of this lane's waves on the grid (At, R) -- fixed for the whole run
+    int slot_pad[kOwn];
+#pragma unroll
+    for (int q = 0; q < kOwn; ++q) slot_pad[q] = gl + q * L < N ? padx<kSk8>(p.slot[gl + q * L]) : 0;
+    const Corr8Lane cl = corr8_lane<L>(M, M, gl);       // both correlations of a stage: M outputs, M terms
+#ifdef FPA_COMB_TIMING
+    long long tk8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_prev8 = clock64();
+#endif
+
+    for (int i = 0; i < n_steps; ++i) {
+        if (p.check && i > 0 && bad == FPA_POINT_OK) {
+            if (__ballot_sync(0xffffffffu, nf) & gmask) bad = i - 1;  // the state produced by step i-1 was not finite
+        }
+        nf = 0;
+        const bool   resync_next = ((i + 1) % kCombResync) == 0;
+        const double z_next = fma((double)(i + 1), h, z0);
+        for (int stage = 0; stage < 4; ++stage) {
+            FPA_TICK8(0);
+            __syncwarp();
+            // ---- X_d = sum_m conj(At[m]) At[m+d], d in [0, M), stored mirrored: Yc[M-1-d] = X_d, Yc[M-1+d] = conj(X_d)
+            corr8<L, PLOG, false>(s.At, s.At, cl, (int)0x80000000, M, Yc, trash);
+            FPA_TICK8(1);
+            __syncwarp();
+            // ---- R_n = sum_k At[k] X_{n-k} = sum_k At[k] Yc[(M-1-n) + k]; output o = M-1-n
+            corr8<L, PLOG, true>(s.At, Yc, cl, 0, M, s.R, trash);
+            FPA_TICK8(2);
+            __syncwarp();
+            // ---- k, RK4 bookkeeping and the next stage's phases / rotated state: one pass per wave, straight-line
+            // code per stage (one uniform jump instead of a chain of stage tests)
+            switch (stage) {
+            case 0:
+#pragma unroll
+                for (int q = 0; q < kOwn; ++q)
+                    if (gl + q * L < N) wave_pass<0>(s, gl + q * L, slot_pad[q], ks, false, 0.0, false, nf);
+                break;
+            case 1:
+#pragma unroll
+                for (int q = 0; q < kOwn; ++q)
+                    if (gl + q * L < N) wave_pass<1>(s, gl + q * L, slot_pad[q], ks, false, 0.0, false, nf);
+                break;
+            case 2:
+#pragma unroll
+                for (int q = 0; q < kOwn; ++q)
+                    if (gl + q * L < N) wave_pass<2>(s, gl + q * L, slot_pad[q], ks, false, 0.0, false, nf);
+                break;
+            default:
+#pragma unroll
+                for (int q = 0; q < kOwn; ++q)
+                    if (gl + q * L < N) wave_pass<3>(s, gl + q * L, slot_pad[q], ks, resync_next, z_next, p.check != 0, nf);
+                break;
+            }
+            FPA_TICK8(3);
+        }
+        if (--save_ctr == 0) {
+            save_ctr = p.save_every;
+            if (tr) {
+                for (int j = gl; j < N; j += L) tr[j] = s.y[j];
+                tr += N;
+            }
+            if (p.Pmax) {
+#pragma unroll
+                for (int q = 0; q < kOwn; ++q) {
+                    const int j = gl + q * L;
+                    if (j < N) {
+                        const double P = fma(s.y[j].y, s.y[j].y, s.y[j].x * s.y[j].x);
+                        pm[q] = (P != P || pm[q] != pm[q]) ? qnan() : fmax(pm[q], P);
+                    }
+                }
+            }
+        }
+    }
+    if (p.check && bad == FPA_POINT_OK) {
+        if (__ballot_sync(0xffffffffu, nf) & gmask) bad = n_steps - 1;
+    }
+#ifdef FPA_COMB_TIMING
+    if (b == 0 && gl == 0) {
+        const double st = 4.0 * n_steps;
+        printf("comb8<L=%d,PLOG=%d> cycles per stage: other %.0f | auto-correlation %.0f | convolution %.0f | wave pass %.0f\n",
+               L, PLOG, tk8[0] / st, tk8[1] / st, tk8[2] / st, tk8[3] / st);
+        printf("   per correlation: setup %.0f | window + terms %.0f | reduce-scatter %.0f | stores %.0f\n", g_corr_ticks[0] / (2 * st),
+               g_corr_ticks[1] / (2 * st), g_corr_ticks[2] / (2 * st), g_corr_ticks[3] / (2 * st));
+        for (int k = 0; k < 8; ++k) g_corr_ticks[k] = 0;
+    }
+#endif
+    if (!real) return;
+    if (p.status && gl == 0) p.status[b] = bad;
+    if (p.A_end) {
+        double2* o = reinterpret_cast<double2*>(p.A_end) + b * N;
+        for (int j = gl; j < N; j += L) o[j] = s.y[j];
+    }
+    if (p.Pmax) {
+#pragma unroll
+        for (int q = 0; q < kOwn; ++q) {
+            const int j = gl + q * L;
+            if (j < N) p.Pmax[b * N + j] = pm[q];
+        }
+    }
+}
+
+template <int L, int PLOG>
+static cudaError_t comb8_launch_p(const CombParams& p, int sms, cudaStream_t st) {
+    constexpr int PPW = 32 / L;
+    const size_t  smem_point = comb_point_doubles(p.n_waves, p.span, kSk8) * sizeof(double);
+    // warps per CTA: as many (up to 8) as fit the shared memory and still leave two CTAs for every SM, so that
+    // a mid-sized batch spreads over the whole chip
+    int wpc = kCombThreads / 32;
+    while (wpc > 1 && (smem_point * PPW * wpc > 200 * 1024 ||
+                       (p.n_points + (int64_t)PPW * wpc - 1) / (PPW * wpc) < 2 * (int64_t)sms))
+        wpc >>= 1;
+    const size_t smem = smem_point * PPW * wpc;
+    cudaError_t  e = cudaFuncSetAttribute(nwave_comb8_kernel<L, PLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)((p.n_points + (int64_t)PPW * wpc - 1) / (PPW * wpc));
+    nwave_comb8_kernel<L, PLOG><<<blocks, 32 * wpc, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// The number of parts of the term range follows from the plan's span (tiles of 8 outputs, L lanes): the usual
+// sizes get the kernel with a compile-time reduce-scatter, everything else the generic one.
+template <int L>
+static cudaError_t comb8_launch(const CombParams& p, int sms, cudaStream_t st) {
+    const int n_tiles = (p.span + 7) >> 3;
+    int       lp = 0;
+    while ((1 << lp) < n_tiles && (1 << lp) < L) ++lp;
+    int plog = 0;
+    while ((1 << (lp + plog)) < L) ++plog;
+    if (plog == 1) return comb8_launch_p<L, 1>(p, sms, st);   // L = 32: span 65..128; L = 16: span 33..64
+    if (plog == 2) return comb8_launch_p<L, 2>(p, sms, st);   // L = 32: span 33..64;  L = 16: span 17..32
+    return comb8_launch_p<L, -1>(p, sms, st);
+}
+
 template <int W, int TILE, int SPLIT>
 static cudaError_t comb_launch_w(const CombParams& p, int sms, cudaStream_t st) {
     const size_t smem_point = comb_point_doubles(p.n_waves, p.span, skew_of(TILE)) * sizeof(double);
@@ -467,11 +940,17 @@ int nwave_comb_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // one warp per point once the batch can give every SM sub-partition a point of its own (and 8 points
     // fit into a CTA's shared memory); below that one CTA per point, for latency
-    const size_t smem_w1 = comb_point_doubles(N, M, skew_of(4)) * sizeof(double);
-    const bool   wide = d->n_points >= 4 * (int64_t)sms && smem_w1 * 8 <= 200 * 1024;
+    const size_t smem_w1 = comb_point_doubles(N, M, kSk8) * sizeof(double);
+    const bool   wide = d->n_points >= 4 * (int64_t)sms && smem_w1 <= 200 * 1024;
+    static const int old_wide = getenv("FPA_COMB_TILE4") ? atoi(getenv("FPA_COMB_TILE4")) : 0;  // tools: round-1 mapping
+    static const int force_l = getenv("FPA_COMB_LANES") ? atoi(getenv("FPA_COMB_LANES")) : 0;  // tools: 32 | 16
+    // half a warp per point once the batch still gives every sub-partition two warps that way
+    const bool half_warp = force_l ? force_l == 16 : d->n_points >= 16 * (int64_t)sms * 4;
     // CTA per point: 4 warps, tiles of 2, sums split 4 ways -- the fastest of the seven (W, TILE, SPLIT)
     // shapes tried for single runs (5.8 us per step at N = 64, 4.3 at N = 21; the others 5.9 .. 7.3)
-    cudaError_t e = wide ? comb_launch_w<1, 4, 2>(p, sms, st) : comb_launch_w<4, 2, 4>(p, sms, st);
+    cudaError_t e = !wide ? comb_launch_w<4, 2, 4>(p, sms, st)
+                    : old_wide ? comb_launch_w<1, 4, 2>(p, sms, st)
+                    : half_warp ? comb8_launch<16>(p, sms, st) : comb8_launch<32>(p, sms, st);
     if (e != cudaSuccess) return cuda_fail(e, "nwave_comb_kernel launch");
     return FPA_OK;
 }

@@ -20,7 +20,7 @@ nw, ds = fpa.nwave, fpa.dispersion
 w0 = 2 * np.pi * 299792458.0 / 1550e-9
 disp = ds.DispersionParams(omega_ref=w0, beta2=-2.57e-29, beta3=3.30e-41, beta4=-1.63e-55)
 with fpa._lib.use_library(out):
-    for N, B in ((8, 1), (64, 1), (64, 4736)):
+    for N, B in ((8, 1), (64, 1), (64, 592), (64, 1024), (64, 4736)):
         plan = nw.uniform_comb_plan(w0, 2 * np.pi * 100e9, range(-(N // 2), N - N // 2))
         beta = nw.beta_per_wave(plan, disp)
         A0 = np.sqrt(np.full((B, N), 1e-3)).astype(complex)
