@@ -530,15 +530,21 @@ struct Corr8Lane {
     int i0, i1, half;    // term range of the part (half: exactly four terms)
     int off, cnt;        // outputs of the tile this lane ends up with
     int rounds, n_tiles, n_out, idle;
+    int tiles_w, tile0;  // tiles of this warp: [tile0, tile0 + tiles_w)
 };
 
+// `gl` = lane within the point's share of ONE warp (L lanes); with W > 1 warps per point, warp `wp` of the
+// point owns the tiles [wp * tiles_w, (wp + 1) * tiles_w) -- all parts of an output live in one warp, so the
+// reduce-scatter never crosses a warp.
 template <int L>
-__device__ __forceinline__ Corr8Lane corr8_lane(int n_terms, int n_out, int gl) {
+__device__ __forceinline__ Corr8Lane corr8_lane(int n_terms, int n_out, int gl, int W = 1, int wp = 0) {
     Corr8Lane c;
     c.n_out = n_out;
     c.n_tiles = (n_out + 7) >> 3;
+    c.tiles_w = (c.n_tiles + W - 1) / W;
+    c.tile0 = wp * c.tiles_w;
     c.lp = 0;
-    while ((1 << c.lp) < c.n_tiles && (1 << c.lp) < L) ++c.lp;
+    while ((1 << c.lp) < c.tiles_w && (1 << c.lp) < L) ++c.lp;
     int parts = L >> c.lp;
     c.parts_log = 0;
     while ((1 << c.parts_log) < parts) ++c.parts_log;
@@ -552,7 +558,7 @@ __device__ __forceinline__ Corr8Lane corr8_lane(int n_terms, int n_out, int gl) 
     const int end8 = (n_terms + 7) & ~7;
     if (c.i1 > end8) c.i1 = end8;
     c.idle = c.i0 >= n_terms;
-    c.rounds = (c.n_tiles + (1 << c.lp) - 1) >> c.lp;
+    c.rounds = (c.tiles_w + (1 << c.lp) - 1) >> c.lp;
     c.off = ((c.part & 1) && c.parts_log >= 1 ? 4 : 0) + ((c.part & 2) && c.parts_log >= 2 ? 2 : 0) +
             ((c.part & 4) && c.parts_log >= 3 ? 1 : 0);
     c.cnt = 8 >> (c.parts_log < 3 ? c.parts_log : 3);
@@ -602,8 +608,8 @@ __device__ __forceinline__ void corr8(const double2* a, const double2* w, const 
     long long ct_prev = clock64();
 #endif
     for (int r = 0; r < c.rounds; ++r) {
-        const int  tile = r * LP + c.tl;
-        const bool live = tile < c.n_tiles && !c.idle;
+        const int  tile = c.tile0 + r * LP + c.tl;
+        const bool live = r * LP + c.tl < c.tiles_w && tile < c.n_tiles && !c.idle;
         double     re[8], im[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) re[t] = im[t] = 0.0;
@@ -626,7 +632,7 @@ __device__ __forceinline__ void corr8(const double2* a, const double2* w, const 
         constexpr int kMaxOut = PLOG < 0 ? 8 : (8 >> (PLOG < 3 ? PLOG : 3));
 #pragma unroll
         for (int t = 0; t < kMaxOut; ++t) {
-            const bool ok = t < c.cnt && o0 + t < c.n_out;
+            const bool ok = t < c.cnt && o0 + t < c.n_out && r * LP + c.tl < c.tiles_w;
             double2* q1 = ok ? dst + padx<kSk8>(M - 1 - (o0 + t)) : trash;
             *q1 = make_double2(re[t], im[t]);
             if (!TO_R) {
@@ -694,16 +700,34 @@ __device__ __forceinline__ void wave_pass(const CombSmem& s, int j, int slot_pad
 // same for the whole batch).  L = 32 for batches that would otherwise leave sub-partitions without a warp;
 // L = 16 halves the shared-memory and shuffle operations per FMA (each lane runs twice as many terms per
 // window and per reduction) and is used once the batch still gives every sub-partition its warps.
-template <int L, int PLOG>
+// Barrier over the W warps of one scan point (W = 1: the warp itself).  Named barriers 1..8 of the CTA.
+template <int W>
+__device__ __forceinline__ void point_sync(int point_in_cta) {
+    if (W == 1)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(point_in_cta + 1), "r"(32 * W) : "memory");
+}
+
+// W = 2 (with L = 32): TWO warps per point, each owning half of the output tiles of both correlations and half
+// of the waves -- for batches of about one point per sub-partition (BASELINE config 5: B = 1024 on 592
+// sub-partitions), where one warp per point leaves the FP64 pipe waiting on that warp's own latencies.
+template <int L, int PLOG, int W>
 __global__ void __launch_bounds__(kCombThreads, L == 32 ? 2 : 1) nwave_comb8_kernel(const CombParams p) {
     extern __shared__ __align__(16) double comb_smem_raw[];
-    constexpr int PPW = 32 / L;              // points per warp
-    constexpr int kOwn = 128 / L;            // waves a lane owns at most (N <= 128)
+    static_assert(W == 1 || L == 32, "several warps per point only with whole warps");
+    constexpr int PPW = 32 / L;              // points per warp (W == 1)
+    constexpr int LW = L * W;                // lanes of a point
+    constexpr int kOwn = 128 / LW;           // waves a lane owns at most (N <= 128)
     const int     N = p.n_waves, M = p.span;
-    const int     lane = threadIdx.x & 31, gl = lane & (L - 1), grp = lane / L;
-    const int     sub = (threadIdx.x >> 5) * PPW + grp;                   // point slot inside the CTA
-    const int64_t b_raw = ((int64_t)blockIdx.x * (blockDim.x >> 5)) * PPW + sub;
-    if (((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PPW >= p.n_points) return;  // whole warps leave
+    const int     lane = threadIdx.x & 31, glw = lane & (L - 1), grp = lane / L;
+    const int     wp = W == 1 ? 0 : (threadIdx.x >> 5) % W;               // warp within the point
+    const int     gl = wp * L + glw;                                      // lane within the point
+    const int     sub = W == 1 ? (threadIdx.x >> 5) * PPW + grp : (threadIdx.x >> 5) / W;   // point slot inside the CTA
+    const int     ppc = W == 1 ? (blockDim.x >> 5) * PPW : (blockDim.x >> 5) / W;           // points per CTA
+    const int64_t b_raw = (int64_t)blockIdx.x * ppc + sub;
+    // whole warps (W == 1) / whole points (W > 1) beyond the batch leave; nobody waits for them
+    if ((W == 1 ? (int64_t)blockIdx.x * ppc + (threadIdx.x >> 5) * PPW : b_raw) >= p.n_points) return;
     // groups of a partly filled last warp run a copy of the last point (lock-step shuffles) and store nothing
     const bool    real = b_raw < p.n_points;
     const int64_t b = real ? b_raw : p.n_points - 1;
@@ -722,14 +746,16 @@ __global__ void __launch_bounds__(kCombThreads, L == 32 ? 2 : 1) nwave_comb8_ker
     ks.h3    = ks.h6 + ks.h6;
 
     const int words = comb_seq_words(M, kSk8);
-    for (int m = gl; m < words; m += L) {
+    for (int m = gl; m < words; m += LW) {
         s.At[m] = make_double2(0.0, 0.0);  // empty grid slots and the padding stay 0
         s.Y[m]  = make_double2(0.0, 0.0);
     }
-    for (int m = gl; m < comb_r_words(M); m += L) s.R[m] = make_double2(0.0, 0.0);
-    __syncwarp();
+    for (int m = gl; m < comb_r_words(M); m += LW) s.R[m] = make_double2(0.0, 0.0);
+    int* const nf_flag = s.slot + ((N + 1) & ~1);       // W > 1: non-finite flags of two consecutive steps
+    if (gl < 2) nf_flag[gl] = 0;
+    point_sync<W>(sub);
     // per-wave state; stage 0 of the first step: exact phase at z0, ys = yn = y, At = y * E
-    for (int j = gl; j < N; j += L) {
+    for (int j = gl; j < N; j += LW) {
         const double bj = p.beta[b * p.beta_stride * N + j];
         s.beta[j] = bj;
         const double2 v = (reinterpret_cast<const double2*>(p.A0) + b * p.A0_stride * N)[j];
@@ -744,33 +770,34 @@ __global__ void __launch_bounds__(kCombThreads, L == 32 ? 2 : 1) nwave_comb8_ker
 
     double2* tr = (p.A_trace && real) ? reinterpret_cast<double2*>(p.A_trace) + b * p.n_saved * N : nullptr;
     if (tr) {
-        for (int j = gl; j < N; j += L) tr[j] = s.y[j];
+        for (int j = gl; j < N; j += LW) tr[j] = s.y[j];
         tr += N;
     }
     double pm[kOwn];
 #pragma unroll
     for (int q = 0; q < kOwn; ++q) {
-        const int j = gl + q * L;
+        const int j = gl + q * LW;
         pm[q] = (p.Pmax && j < N) ? fma(s.y[j].y, s.y[j].y, s.y[j].x * s.y[j].x) : 0.0;
     }
     int      save_ctr = p.save_every;
     int32_t  bad = FPA_POINT_OK;
     int      nf = 0;                                    // a component of the state entering the step is not finite
     if (p.check)
-        for (int j = gl; j < N; j += L) nf |= (nonfinite(s.y[j].x) || nonfinite(s.y[j].y)) ? 1 : 0;
+        for (int j = gl; j < N; j += LW) nf |= (nonfinite(s.y[j].x) || nonfinite(s.y[j].y)) ? 1 : 0;
+    if (W > 1 && nf) nf_flag[1] = 1;                    // "step -1" has odd parity
     double2* const Yc = s.Y;                            // Yc[padx(q)] = X_{M-1-q}, q in [0, 2M-2]
     double2* const trash = s.R + comb_r_words(M) - 1;   // spare word: target of the stores of lanes without an output
     // padded positions of this lane's waves on the grid (At, R) -- fixed for the whole run
     int slot_pad[kOwn];
 #pragma unroll
-    for (int q = 0; q < kOwn; ++q) slot_pad[q] = gl + q * L < N ? padx<kSk8>(p.slot[gl + q * L]) : 0;
-    const Corr8Lane cl = corr8_lane<L>(M, M, gl);       // both correlations of a stage: M outputs, M terms
+    for (int q = 0; q < kOwn; ++q) slot_pad[q] = gl + q * LW < N ? padx<kSk8>(p.slot[gl + q * LW]) : 0;
+    const Corr8Lane cl = corr8_lane<L>(M, M, glw, W, wp);   // both correlations of a stage: M outputs, M terms
 #ifdef FPA_COMB_TIMING
     long long tk8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_prev8 = clock64();
 #endif
 
     for (int i = 0; i < n_steps; ++i) {
-        if (p.check && i > 0 && bad == FPA_POINT_OK) {
+        if (W == 1 && p.check && i > 0 && bad == FPA_POINT_OK) {
             if (__ballot_sync(0xffffffffu, nf) & gmask) bad = i - 1;  // the state produced by step i-1 was not finite
         }
         nf = 0;
@@ -778,51 +805,56 @@ __global__ void __launch_bounds__(kCombThreads, L == 32 ? 2 : 1) nwave_comb8_ker
         const double z_next = fma((double)(i + 1), h, z0);
         for (int stage = 0; stage < 4; ++stage) {
             FPA_TICK8(0);
-            __syncwarp();
+            point_sync<W>(sub);
+            if (W > 1 && stage == 0 && p.check) {   // flag written by either warp in the last pass of step i-1
+                if (i > 0 && bad == FPA_POINT_OK && nf_flag[(i - 1) & 1]) bad = i - 1;
+            }
             // ---- X_d = sum_m conj(At[m]) At[m+d], d in [0, M), stored mirrored: Yc[M-1-d] = X_d, Yc[M-1+d] = conj(X_d)
             corr8<L, PLOG, false>(s.At, s.At, cl, (int)0x80000000, M, Yc, trash);
             FPA_TICK8(1);
-            __syncwarp();
+            point_sync<W>(sub);
+            if (W > 1 && stage == 0 && gl == 0) nf_flag[i & 1] = 0;   // everybody has read step i-1's flag; clear this step's
             // ---- R_n = sum_k At[k] X_{n-k} = sum_k At[k] Yc[(M-1-n) + k]; output o = M-1-n
             corr8<L, PLOG, true>(s.At, Yc, cl, 0, M, s.R, trash);
             FPA_TICK8(2);
-            __syncwarp();
+            point_sync<W>(sub);
             // ---- k, RK4 bookkeeping and the next stage's phases / rotated state: one pass per wave, straight-line
             // code per stage (one uniform jump instead of a chain of stage tests)
             switch (stage) {
             case 0:
 #pragma unroll
                 for (int q = 0; q < kOwn; ++q)
-                    if (gl + q * L < N) wave_pass<0>(s, gl + q * L, slot_pad[q], ks, false, 0.0, false, nf);
+                    if (gl + q * LW < N) wave_pass<0>(s, gl + q * LW, slot_pad[q], ks, false, 0.0, false, nf);
                 break;
             case 1:
 #pragma unroll
                 for (int q = 0; q < kOwn; ++q)
-                    if (gl + q * L < N) wave_pass<1>(s, gl + q * L, slot_pad[q], ks, false, 0.0, false, nf);
+                    if (gl + q * LW < N) wave_pass<1>(s, gl + q * LW, slot_pad[q], ks, false, 0.0, false, nf);
                 break;
             case 2:
 #pragma unroll
                 for (int q = 0; q < kOwn; ++q)
-                    if (gl + q * L < N) wave_pass<2>(s, gl + q * L, slot_pad[q], ks, false, 0.0, false, nf);
+                    if (gl + q * LW < N) wave_pass<2>(s, gl + q * LW, slot_pad[q], ks, false, 0.0, false, nf);
                 break;
             default:
 #pragma unroll
                 for (int q = 0; q < kOwn; ++q)
-                    if (gl + q * L < N) wave_pass<3>(s, gl + q * L, slot_pad[q], ks, resync_next, z_next, p.check != 0, nf);
+                    if (gl + q * LW < N) wave_pass<3>(s, gl + q * LW, slot_pad[q], ks, resync_next, z_next, p.check != 0, nf);
                 break;
             }
+            if (W > 1 && stage == 3 && nf) nf_flag[i & 1] = 1;
             FPA_TICK8(3);
         }
         if (--save_ctr == 0) {
             save_ctr = p.save_every;
             if (tr) {
-                for (int j = gl; j < N; j += L) tr[j] = s.y[j];
+                for (int j = gl; j < N; j += LW) tr[j] = s.y[j];
                 tr += N;
             }
             if (p.Pmax) {
 #pragma unroll
                 for (int q = 0; q < kOwn; ++q) {
-                    const int j = gl + q * L;
+                    const int j = gl + q * LW;
                     if (j < N) {
                         const double P = fma(s.y[j].y, s.y[j].y, s.y[j].x * s.y[j].x);
                         pm[q] = (P != P || pm[q] != pm[q]) ? qnan() : fmax(pm[q], P);
@@ -831,14 +863,17 @@ __global__ void __launch_bounds__(kCombThreads, L == 32 ? 2 : 1) nwave_comb8_ker
             }
         }
     }
-    if (p.check && bad == FPA_POINT_OK) {
+    if (W > 1) {
+        point_sync<W>(sub);
+        if (p.check && bad == FPA_POINT_OK && nf_flag[(n_steps - 1) & 1]) bad = n_steps - 1;
+    } else if (p.check && bad == FPA_POINT_OK) {
         if (__ballot_sync(0xffffffffu, nf) & gmask) bad = n_steps - 1;
     }
 #ifdef FPA_COMB_TIMING
     if (b == 0 && gl == 0) {
         const double st = 4.0 * n_steps;
-        printf("comb8<L=%d,PLOG=%d> cycles per stage: other %.0f | auto-correlation %.0f | convolution %.0f | wave pass %.0f\n",
-               L, PLOG, tk8[0] / st, tk8[1] / st, tk8[2] / st, tk8[3] / st);
+        printf("comb8<L=%d,PLOG=%d,W=%d> cycles per stage: other %.0f | auto-correlation %.0f | convolution %.0f | wave pass %.0f\n",
+               L, PLOG, W, tk8[0] / st, tk8[1] / st, tk8[2] / st, tk8[3] / st);
         printf("   per correlation: setup %.0f | window + terms %.0f | reduce-scatter %.0f | stores %.0f\n", g_corr_ticks[0] / (2 * st),
                g_corr_ticks[1] / (2 * st), g_corr_ticks[2] / (2 * st), g_corr_ticks[3] / (2 * st));
         for (int k = 0; k < 8; ++k) g_corr_ticks[k] = 0;
@@ -848,47 +883,53 @@ __global__ void __launch_bounds__(kCombThreads, L == 32 ? 2 : 1) nwave_comb8_ker
     if (p.status && gl == 0) p.status[b] = bad;
     if (p.A_end) {
         double2* o = reinterpret_cast<double2*>(p.A_end) + b * N;
-        for (int j = gl; j < N; j += L) o[j] = s.y[j];
+        for (int j = gl; j < N; j += LW) o[j] = s.y[j];
     }
     if (p.Pmax) {
 #pragma unroll
         for (int q = 0; q < kOwn; ++q) {
-            const int j = gl + q * L;
+            const int j = gl + q * LW;
             if (j < N) p.Pmax[b * N + j] = pm[q];
         }
     }
 }
 
-template <int L, int PLOG>
+template <int L, int PLOG, int W>
 static cudaError_t comb8_launch_p(const CombParams& p, int sms, cudaStream_t st) {
     constexpr int PPW = 32 / L;
     const size_t  smem_point = comb_point_doubles(p.n_waves, p.span, kSk8) * sizeof(double);
     // warps per CTA: as many (up to 8) as fit the shared memory and still leave two CTAs for every SM, so that
-    // a mid-sized batch spreads over the whole chip
+    // a mid-sized batch spreads over the whole chip; points per CTA = wpc * PPW (W = 1) or wpc / W
     int wpc = kCombThreads / 32;
-    while (wpc > 1 && (smem_point * PPW * wpc > 200 * 1024 ||
-                       (p.n_points + (int64_t)PPW * wpc - 1) / (PPW * wpc) < 2 * (int64_t)sms))
+    auto points = [&](int w) { return W == 1 ? w * PPW : w / W; };
+    while (wpc > W && (smem_point * points(wpc) > 200 * 1024 ||
+                       (p.n_points + points(wpc) - 1) / points(wpc) < 2 * (int64_t)sms))
         wpc >>= 1;
-    const size_t smem = smem_point * PPW * wpc;
-    cudaError_t  e = cudaFuncSetAttribute(nwave_comb8_kernel<L, PLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = smem_point * points(wpc);
+    cudaError_t  e = cudaFuncSetAttribute(nwave_comb8_kernel<L, PLOG, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const unsigned blocks = (unsigned)((p.n_points + (int64_t)PPW * wpc - 1) / (PPW * wpc));
-    nwave_comb8_kernel<L, PLOG><<<blocks, 32 * wpc, smem, st>>>(p);
+    const unsigned blocks = (unsigned)((p.n_points + points(wpc) - 1) / points(wpc));
+    nwave_comb8_kernel<L, PLOG, W><<<blocks, 32 * wpc, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-// The number of parts of the term range follows from the plan's span (tiles of 8 outputs, L lanes): the usual
-// sizes get the kernel with a compile-time reduce-scatter, everything else the generic one.
-template <int L>
+// The number of parts of the term range follows from the plan's span (tiles of 8 outputs, L lanes, W warps
+// sharing the tiles): the usual sizes get the kernel with a compile-time reduce-scatter, everything else the
+// generic one.
+template <int L, int W>
 static cudaError_t comb8_launch(const CombParams& p, int sms, cudaStream_t st) {
-    const int n_tiles = (p.span + 7) >> 3;
+    const int tiles_w = (((p.span + 7) >> 3) + W - 1) / W;
     int       lp = 0;
-    while ((1 << lp) < n_tiles && (1 << lp) < L) ++lp;
+    while ((1 << lp) < tiles_w && (1 << lp) < L) ++lp;
     int plog = 0;
     while ((1 << (lp + plog)) < L) ++plog;
-    if (plog == 1) return comb8_launch_p<L, 1>(p, sms, st);   // L = 32: span 65..128; L = 16: span 33..64
-    if (plog == 2) return comb8_launch_p<L, 2>(p, sms, st);   // L = 32: span 33..64;  L = 16: span 17..32
-    return comb8_launch_p<L, -1>(p, sms, st);
+    if constexpr (W == 1) {
+        if (plog == 1) return comb8_launch_p<L, 1, W>(p, sms, st);   // L = 32: span 65..128; L = 16: span 33..64
+        if (plog == 2) return comb8_launch_p<L, 2, W>(p, sms, st);   // L = 32: span 33..64;  L = 16: span 17..32
+    } else {
+        if (plog == 3) return comb8_launch_p<L, 3, W>(p, sms, st);   // two warps per point: span 33..64
+    }
+    return comb8_launch_p<L, -1, W>(p, sms, st);
 }
 
 template <int W, int TILE, int SPLIT>
@@ -944,13 +985,15 @@ int nwave_comb_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     const bool   wide = d->n_points >= 4 * (int64_t)sms && smem_w1 <= 200 * 1024;
     static const int old_wide = getenv("FPA_COMB_TILE4") ? atoi(getenv("FPA_COMB_TILE4")) : 0;  // tools: round-1 mapping
     static const int force_l = getenv("FPA_COMB_LANES") ? atoi(getenv("FPA_COMB_LANES")) : 0;  // tools: 32 | 16
-    // half a warp per point once the batch still gives every sub-partition two warps that way
-    const bool half_warp = force_l ? force_l == 16 : d->n_points >= 16 * (int64_t)sms * 4;
+    // lanes per point: half a warp once the batch still gives every sub-partition two warps that way.  (Two
+    // warps per point -- the W = 2 instantiation of the kernel, tiles split over the warps, named barriers -- was
+    // measured for the small batches and lost: B = 1024 5.8e7 against 6.6e7 point.steps/s, B = 592 5.8e7 against 6.3e7.)
+    const int lanes = force_l ? force_l : d->n_points >= 16 * (int64_t)sms * 4 ? 16 : 32;
     // CTA per point: 4 warps, tiles of 2, sums split 4 ways -- the fastest of the seven (W, TILE, SPLIT)
     // shapes tried for single runs (5.8 us per step at N = 64, 4.3 at N = 21; the others 5.9 .. 7.3)
     cudaError_t e = !wide ? comb_launch_w<4, 2, 4>(p, sms, st)
                     : old_wide ? comb_launch_w<1, 4, 2>(p, sms, st)
-                    : half_warp ? comb8_launch<16>(p, sms, st) : comb8_launch<32>(p, sms, st);
+                    : lanes == 16 ? comb8_launch<16, 1>(p, sms, st) : comb8_launch<32, 1>(p, sms, st);
     if (e != cudaSuccess) return cuda_fail(e, "nwave_comb_kernel launch");
     return FPA_OK;
 }

@@ -204,12 +204,8 @@ def branch_target(x):
     return int(m.group(1), 16) if m else None
 
 
-def hot_loop(ins, min_fp64=24):
-    """(lo, hi) addresses of the z-loop: the backward-branch span with the most FP64 instructions among
-    the spans that hold no other FP64-carrying loop (>= min_fp64 FP64 instructions) inside them.  For a
-    kernel whose only big loop is the z-loop that is the largest backward span; in the persistent kernels
-    (a work-item loop around prologue + z-loop) it is still the z-loop, so the per-item prologue with its
-    unrolled double-double powers is never touched."""
+def _leaf_loops(ins, min_fp64=24):
+    """Backward-branch spans (lo, hi, n_fp64) that hold no other FP64-carrying loop inside them."""
     spans = []
     for x in ins:
         if x.base == "BRA":
@@ -217,8 +213,26 @@ def hot_loop(ins, min_fp64=24):
             if tgt is not None and tgt < x.addr:
                 n = sum(1 for y in ins if y.is_fp64 and tgt <= y.addr <= x.addr)
                 spans.append((tgt, x.addr, n))
-    leaves = [s for s in spans if s[2] > 0 and not any(
+    return [s for s in spans if s[2] > 0 and not any(
         o is not s and s[0] <= o[0] and o[1] <= s[1] and o[2] >= min_fp64 for o in spans)]
+
+
+def hot_loops(ins, min_fp64=24):
+    """The hot loops of a kernel: the innermost loop with the most FP64 instructions -- the z-loop of the RK4
+    kernels -- and every other innermost loop within 20 % of its FP64 count (the N-wave comb kernel runs the
+    same unrolled correlation body in two places).  For a kernel whose only big loop is the z-loop that is
+    the largest backward span; in the persistent kernels (a work-item loop around prologue + z-loop) it is
+    still the z-loop, so the per-item prologue with its unrolled double-double powers is never touched."""
+    leaves = _leaf_loops(ins, min_fp64)
+    if not leaves:
+        return []
+    top = max(s[2] for s in leaves)
+    return sorted((s[0], s[1]) for s in leaves if 5 * s[2] >= 4 * top)
+
+
+def hot_loop(ins, min_fp64=24):
+    """(lo, hi) of the FP64-richest innermost loop, (0, 0) when the kernel has none."""
+    leaves = _leaf_loops(ins, min_fp64)
     if not leaves:
         return (0, 0)
     lo, hi, _ = max(leaves, key=lambda s: (s[2], s[1] - s[0]))
@@ -226,12 +240,15 @@ def hot_loop(ins, min_fp64=24):
 
 
 def hot_blocks(ins, min_fp64=24):
-    """Straight-line runs inside the z-loop with at least min_fp64 FP64 instructions (index lists)."""
-    lo, hi = hot_loop(ins)
+    """Straight-line runs inside the hot loops with at least min_fp64 FP64 instructions (index lists)."""
+    loops = hot_loops(ins, min_fp64)
     targets = {branch_target(x) for x in ins} - {None}
     blocks, cur = [], []
     for i, x in enumerate(ins):
-        if not (lo <= x.addr <= hi):
+        if not any(lo <= x.addr <= hi for lo, hi in loops):
+            if cur:
+                blocks.append(cur)
+                cur = []
             continue
         if x.addr in targets and cur:
             blocks.append(cur)
