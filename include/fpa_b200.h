@@ -49,6 +49,12 @@ extern "C" {
                                     * the constant-h / phase-recurrence fast kernel) */
 #define FPA_NWAVE_TABLE (1u << 6)   /* N-wave: force the enumerated-triplet kernel even   *
                                     * when grid_slot is given                          */
+#define FPA_NWAVE_COMB  (1u << 7)   /* N-wave: insist on the convolution-form kernel     *
+                                    * (FPA_ERR_UNSUPPORTED beyond its limits); without  *
+                                    * either flag the library picks: convolution form   *
+                                    * for grid plans within its limits (span <= 512)    *
+                                    * unless the plan is so sparse that the table has   *
+                                    * less work (span^2 > 5 * n_triplets)               */
 #define FPA_UNIFORM_PHYSICS (1u << 5) /* gamma and alpha are the same for every point *
                                     * (stride 0) AND their values are given in       *
                                     * gamma_uniform / alpha_uniform: the kernel then  *
@@ -264,6 +270,14 @@ typedef struct fpa_triplet {
 int64_t fpa_enumerate_triplets(int32_t N, const int32_t* g, fpa_triplet* out, int64_t cap,
                                int64_t* row_ptr);
 
+/* The same for a plan that is NOT on an integer grid: entry (n;k,l,m) exists iff the photon energies match
+ * within the reference's tolerance rule for its four-wave plan (frequency_plan.enforce_energy_conservation,
+ * frequency_plan.py:112-131: numpy.isclose(w_k + w_l, w_m + w_n, atol, rtol), i.e.
+ * |lhs - rhs| <= atol + rtol * |rhs| with both sums rounded to double first; defaults atol 0, rtol 1e-12).
+ * Same canonical order (n, k <= l, m not in {k, l}) and weights; bit-exact against the CPU restatement. */
+int64_t fpa_enumerate_triplets_omega(int32_t N, const double* omega, double atol, double rtol, fpa_triplet* out,
+                                     int64_t cap, int64_t* row_ptr);
+
 typedef struct fpa_nwave_desc {
     int64_t            n_points;     /* B                                                  */
     int32_t            n_waves;      /* N (<= 128)                                         */
@@ -288,7 +302,9 @@ typedef struct fpa_nwave_desc {
     /* Integer-grid plans (uniform combs): grid_slot[j] = g_j - g_min for every wave, grid_span =
      * g_max - g_min + 1 (<= 512).  When set (and FPA_NWAVE_TABLE is not), the integrator uses the
      * O(span^2) convolution form of the same ODE instead of the enumerated table (csrc/nwave_comb.cu);
-     * triplets / row_ptr may then be NULL. */
+     * triplets / row_ptr may then be NULL -- but when they are given too, plans the convolution form
+     * does not suit (span > 512, or sparse: span^2 > 5 * n_triplets) run through the table kernel.
+     * Slots must be distinct values in [0, grid_span). */
     const int32_t*     grid_slot;    /* [N] or NULL                                        */
     int32_t            grid_span;
     int32_t            reserved2;
@@ -296,6 +312,11 @@ typedef struct fpa_nwave_desc {
 
 int fpa_nwave_rk4_batch_dev(const fpa_nwave_desc* d, void* stream);
 int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device);
+/* The same batch split over several devices of one box from ONE process (BASELINE config 5: B = 1024 pump
+ * powers over the 8 GPUs): contiguous balanced point ranges, one kernel per device in flight at once, every
+ * device writes its own shard of the caller's host arrays.  Bit-identical to the single-device call as long
+ * as every shard stays on the same side of the library's kernel choices (they depend on the batch size). */
+int fpa_nwave_rk4_batch_multi_host(const fpa_nwave_desc* d, int n_devices, const int* devices);
 /* Algorithmic flops per point.step the N-wave kernel is credited with. */
 double fpa_nwave_flops_per_step(int32_t n_waves, int64_t n_triplets, int64_t n_pairs);
 /* Same for the convolution-form kernel (O(span^2) work: credited with what it executes). */

@@ -39,6 +39,27 @@ def enumerate_triplets(grid_index):
     return table, rows
 
 
+def enumerate_triplets_omega(omega, atol=0.0, rtol=1e-12):
+    """Entries (n; k <= l, m not in {k, l}) whose photon energies match under the reference's own rule for its
+    four-wave plan, numpy.isclose(w_k + w_l, w_m + w_n, atol=atol, rtol=rtol)
+    (frequency_plan.enforce_energy_conservation, frequency_plan.py:112-131).  Canonical order n, k, l, m."""
+    w = np.asarray(omega, dtype=float).reshape(-1)
+    N = w.size
+    table, rows = [], [0]
+    for n in range(N):
+        for k in range(N):
+            lhs = w[k] + w[k:]                      # l = k .. N-1
+            rhs = w + w[n]                          # m = 0 .. N-1
+            ok = np.isclose(lhs[:, None], rhs[None, :], atol=atol, rtol=rtol)
+            for dl, m in zip(*np.nonzero(ok)):
+                l = k + int(dl)
+                if m == k or m == l:
+                    continue
+                table.append((k, l, int(m), 1 if k == l else 2))
+        rows.append(len(table))
+    return table, rows
+
+
 def count_ordered(grid_index):
     """(ordered combinations incl. Kerr, non-Kerr ordered, distinct (k,l) pairs) -- the known
     answers quoted in SURVEY App. C (N=4 uniform: 44 / 16 / 6 pairs, 10 table entries)."""

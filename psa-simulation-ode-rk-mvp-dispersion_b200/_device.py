@@ -227,12 +227,31 @@ def enumerate_triplets(grid_index) -> tuple[np.ndarray, np.ndarray]:
     return table, rows
 
 
+def enumerate_triplets_omega(omega, atol: float = 0.0, rtol: float = 1e-12) -> tuple[np.ndarray, np.ndarray]:
+    """(table, row_ptr) of a plan that is not on an integer grid: photon-energy matching with the reference's
+    tolerance rule (`fpa_enumerate_triplets_omega`)."""
+    w = f64(omega).reshape(-1)
+    N = w.size
+    L = _lib.lib()
+    count = L.fpa_enumerate_triplets_omega(N, ptr(w), float(atol), float(rtol), None, 0, None)
+    if count < 0:
+        raise ValueError(_lib.last_error())
+    table = np.empty(count, dtype=_lib.TRIPLET_DTYPE)
+    rows = np.empty(N + 1, dtype=np.int64)
+    got = L.fpa_enumerate_triplets_omega(N, ptr(w), float(atol), float(rtol), ptr(table) if count else None, count, ptr(rows))
+    if got != count:
+        raise ValueError(_lib.last_error())
+    return table, rows
+
+
 def nwave_batch(beta, gamma, alpha, A0, table, row_ptr, *, z0=0.0, z_max, n_steps, save_every=1,
                 trace=False, end=True, pmax=False, check_nan=True, n_points: Optional[int] = None,
-                grid_index=None, force_table: bool = False, device: Optional[int] = None) -> dict:
-    """B points of the N-wave model through `fpa_nwave_rk4_batch_host`.  With `grid_index` (integer
-    grid position of every wave) the library integrates the convolution form of the same ODE
-    (O(span^2) per RHS) unless `force_table` asks for the enumerated-triplet kernel."""
+                grid_index=None, force_table: bool = False, force_comb: bool = False,
+                device: Optional[int] = None, devices=None) -> dict:
+    """B points of the N-wave model through `fpa_nwave_rk4_batch_host` (`devices=[...]`:
+    `fpa_nwave_rk4_batch_multi_host`).  With `grid_index` (integer grid position of every wave) the
+    library may integrate the convolution form of the same ODE (O(span^2) per RHS): it does so for plans
+    within that kernel's limits unless they are sparse; `force_table` / `force_comb` override the choice."""
     A0 = c128(A0)
     N = A0.shape[-1]
     beta = f64(beta)
@@ -261,7 +280,8 @@ def nwave_batch(beta, gamma, alpha, A0, table, row_ptr, *, z0=0.0, z_max, n_step
     d.A0, d.A0_stride = ptr(a0), a0s
     d.triplets, d.row_ptr, d.n_triplets = (ptr(table) if table.size else None), ptr(rows), table.size
     d.z0, d.z_max, d.n_steps, d.save_every = float(z0), float(z_max), n_steps, save_every
-    d.flags = _flags(trace, end, pmax, check_nan, False) | (_lib.NWAVE_TABLE if force_table else 0)
+    d.flags = (_flags(trace, end, pmax, check_nan, False) | (_lib.NWAVE_TABLE if force_table else 0) |
+               (_lib.NWAVE_COMB if force_comb else 0))
     d.A_trace, d.A_end, d.Pmax = ptr(out.get("A_trace")), ptr(out.get("A_end")), ptr(out.get("Pmax"))
     d.status = ptr(out["status"])
     slots = None
@@ -271,7 +291,13 @@ def nwave_batch(beta, gamma, alpha, A0, table, row_ptr, *, z0=0.0, z_max, n_step
             raise ValueError("grid_index must hold one entry per wave")
         slots = np.ascontiguousarray(g - g.min(), dtype=np.int32)
         d.grid_slot, d.grid_span = ptr(slots), int(g.max() - g.min() + 1)
+    if devices is not None and len(devices) > 1:
+        ids = (C.c_int * len(devices))(*[int(v) for v in devices])
+        _lib.check(_lib.lib().fpa_nwave_rk4_batch_multi_host(C.byref(d), len(devices), ids))
+        return out
     dev = _lib.get_device() if device is None else int(device)
+    if devices is not None and len(devices) == 1:
+        dev = int(devices[0])
     _lib.check(_lib.lib().fpa_nwave_rk4_batch_host(C.byref(d), dev))
     return out
 

@@ -18,7 +18,7 @@ LIB_PATH = PKG_DIR / "libfpa_b200.so"
 
 # status codes / flags (include/fpa_b200.h)
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
-OUT_TRACE, OUT_END, OUT_PMAX, CHECK_NAN, PHASE_EXACT, UNIFORM_PHYSICS, NWAVE_TABLE = 1, 2, 4, 8, 16, 32, 64
+OUT_TRACE, OUT_END, OUT_PMAX, CHECK_NAN, PHASE_EXACT, UNIFORM_PHYSICS, NWAVE_TABLE, NWAVE_COMB = 1, 2, 4, 8, 16, 32, 64, 128
 POINT_OK = -1
 PM_GENERAL_TAYLOR, PM_SYMMETRIC_EVEN, PM_PROVIDED = 0, 1, 2
 MAX_TAYLOR_ORDER = 12
@@ -123,6 +123,9 @@ SIGNATURES = {
                                             C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_uint32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fpa_enumerate_triplets": (C.c_int64, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fpa_enumerate_triplets_omega": (C.c_int64, [C.c_int32, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64,
+                                                 C.c_void_p]),
+    "fpa_nwave_rk4_batch_multi_host": (C.c_int, [C.POINTER(NwaveDesc), C.c_int, C.POINTER(C.c_int)]),
     "fpa_nwave_rk4_batch_dev": (C.c_int, [C.POINTER(NwaveDesc), C.c_void_p]),
     "fpa_nwave_rk4_batch_host": (C.c_int, [C.POINTER(NwaveDesc), C.c_int]),
     "fpa_nwave_flops_per_step": (C.c_double, [C.c_int32, C.c_int64, C.c_int64]),

@@ -12,6 +12,7 @@
 
 #include <map>
 #include <tuple>
+#include <vector>
 
 namespace fpa {
 
@@ -148,8 +149,17 @@ static int host_stream(int device, cudaStream_t* st) {
 }
 
 // ----------------------------------------------------------------- N-wave dispatch
+// Which kernel integrates an N-wave batch: the convolution form needs an integer-grid plan within its limits
+// (n_waves <= 128, span <= 512) and pays off unless the plan is sparse (2*span^2 complex MACs per RHS against
+// ~one per table entry; the table kernel gathers, so it is given a factor: span^2 > 5 * n_triplets -> table).
+// FPA_NWAVE_TABLE / FPA_NWAVE_COMB force the choice; a forced comb beyond its limits is FPA_ERR_UNSUPPORTED.
 static bool nwave_use_comb(const fpa_nwave_desc* d) {
-    return d->grid_slot != nullptr && !(d->flags & FPA_NWAVE_TABLE);
+    if (d->grid_slot == nullptr || (d->flags & FPA_NWAVE_TABLE)) return false;
+    if (d->flags & FPA_NWAVE_COMB) return true;
+    const bool table_given = d->row_ptr != nullptr && (d->n_triplets == 0 || d->triplets != nullptr);
+    if (!table_given) return true;
+    if (d->n_waves > 128 || d->grid_span > 512) return false;
+    return (int64_t)d->grid_span * d->grid_span <= 5 * d->n_triplets || d->n_triplets == 0;
 }
 
 static int nwave_dispatch(const fpa_nwave_desc* d, cudaStream_t st) {
@@ -731,36 +741,63 @@ int fpa_nwave_rk4_batch_dev(const fpa_nwave_desc* d, void* stream) {
     return nwave_dispatch(d, static_cast<cudaStream_t>(stream));
 }
 
-int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device) {
+struct PendingNwave {
+    cudaStream_t st = nullptr;
+    size_t       B = 0, N = 0, n_tr = 0;
+    double * tr = nullptr, *Ae = nullptr, *Pm = nullptr;
+    int32_t* stt = nullptr;
+    fpa_nwave_desc user;
+};
+
+static int nwave_host_check(const fpa_nwave_desc* d) {
     FPA_REQUIRE(d != nullptr, "descriptor is NULL");
     FPA_REQUIRE(d->n_points >= 0, "n_points must be >= 0");
     FPA_REQUIRE(d->n_waves >= 1, "n_waves must be >= 1");
     FPA_REQUIRE(d->n_steps >= 1, "n_steps must be >= 1");
     FPA_REQUIRE(d->save_every >= 1, "save_every must be a positive integer");
     FPA_REQUIRE(d->beta && d->gamma && d->alpha && d->A0, "beta/gamma/alpha/A0 must be set");
+    FPA_REQUIRE(!((d->flags & FPA_NWAVE_TABLE) && (d->flags & FPA_NWAVE_COMB)), "FPA_NWAVE_TABLE and FPA_NWAVE_COMB exclude each other");
+    FPA_REQUIRE(!(d->flags & FPA_NWAVE_COMB) || d->grid_slot, "FPA_NWAVE_COMB needs grid_slot");
     const bool comb = nwave_use_comb(d);
     FPA_REQUIRE(comb || (d->n_triplets >= 0 && d->row_ptr), "triplet table must be set");
     FPA_REQUIRE((d->gamma_stride | 1) == 1 && (d->alpha_stride | 1) == 1 && (d->A0_stride | 1) == 1 &&
                     (d->beta_stride | 1) == 1,
                 "strides must be 0 (broadcast) or 1 (per point)");
+    FPA_REQUIRE(!(d->flags & FPA_OUT_TRACE) || d->A_trace, "FPA_OUT_TRACE needs A_trace");
+    FPA_REQUIRE(!(d->flags & FPA_OUT_PMAX) || d->Pmax, "FPA_OUT_PMAX needs Pmax");
+    FPA_REQUIRE(!(d->flags & FPA_OUT_END) || d->A_end, "FPA_OUT_END needs A_end");
+    if (d->grid_slot) {   // host pointers here: the slots can be checked
+        FPA_REQUIRE(d->grid_span >= 1, "grid_span must be >= 1");
+        std::vector<char> seen((size_t)d->grid_span, 0);
+        for (int j = 0; j < d->n_waves; ++j) {
+            const int32_t g = d->grid_slot[j];
+            FPA_REQUIRE(g >= 0 && g < d->grid_span, "grid_slot[%d] = %d is outside [0, grid_span = %d)", j, g, d->grid_span);
+            FPA_REQUIRE(!seen[(size_t)g], "grid_slot values must be distinct (slot %d appears twice)", g);
+            seen[(size_t)g] = 1;
+        }
+    }
+    return FPA_OK;
+}
+
+static int nwave_host_launch(const fpa_nwave_desc* d, int device, PendingNwave* pn) {
+    FPA_TRY(nwave_host_check(d));
+    const bool comb = nwave_use_comb(d);
     const bool trace = (d->flags & FPA_OUT_TRACE) != 0, endo = (d->flags & FPA_OUT_END) != 0;
     const bool pmax = (d->flags & FPA_OUT_PMAX) != 0;
-    FPA_REQUIRE(!trace || d->A_trace, "FPA_OUT_TRACE needs A_trace");
-    FPA_REQUIRE(!pmax || d->Pmax, "FPA_OUT_PMAX needs Pmax");
-    FPA_REQUIRE(!endo || d->A_end, "FPA_OUT_END needs A_end");
     FPA_TRY(use_device(device));
+    *pn = PendingNwave();
     const size_t B = (size_t)d->n_points, N = (size_t)d->n_waves;
     if (B == 0) return FPA_OK;
     const size_t ns = (size_t)fpa_n_saved(d->n_steps, d->save_every);
     const size_t n_b = (d->beta_stride ? B : 1) * N, n_g = d->gamma_stride ? B : 1;
     const size_t n_a = d->alpha_stride ? B : 1, n_A0 = (d->A0_stride ? B : 1) * N * 2;
-    const size_t n_t = comb ? 0 : (size_t)d->n_triplets, n_grid = 0;
+    const size_t n_t = comb ? 0 : (size_t)d->n_triplets;
     const size_t n_tr = trace ? B * ns * N * 2 : 0;
     void* ws = nullptr;
     FPA_TRY(workspace(device, 5,
                       Carver::need(n_b * 8) + Carver::need(n_g * 8) + Carver::need(n_a * 8) +
                           Carver::need(n_A0 * 8) + Carver::need(n_t * sizeof(fpa_triplet)) +
-                          Carver::need((N + 1) * 8) + Carver::need(n_grid * 8) + Carver::need(n_tr * 8) +
+                          Carver::need((N + 1) * 8) + Carver::need(n_tr * 8) +
                           Carver::need(B * N * 16) + Carver::need(B * N * 8) + Carver::need(B * 4) +
                           Carver::need(N * 4),
                       &ws));
@@ -800,13 +837,64 @@ int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device) {
     dd.Pmax     = pmax ? Pm : nullptr;
     dd.status   = stt;
     dd.grid_slot = comb ? slot : nullptr;
+    dd.flags = (d->flags & ~(FPA_NWAVE_TABLE | FPA_NWAVE_COMB)) | (comb ? FPA_NWAVE_COMB : FPA_NWAVE_TABLE);  // decided above
     FPA_TRY(nwave_dispatch(&dd, st));
-    if (trace) FPA_TRY(down(d->A_trace, tr, n_tr * 8, st));
-    if (endo) FPA_TRY(down(d->A_end, Ae, B * N * 16, st));
-    if (pmax) FPA_TRY(down(d->Pmax, Pm, B * N * 8, st));
-    FPA_TRY(down(d->status, stt, B * 4, st));
-    FPA_CUDA(cudaStreamSynchronize(st));
+    pn->st   = st;
+    pn->B    = B;
+    pn->N    = N;
+    pn->n_tr = n_tr;
+    pn->user = *d;
+    pn->tr   = trace ? tr : nullptr;
+    pn->Ae   = endo ? Ae : nullptr;
+    pn->Pm   = pmax ? Pm : nullptr;
+    pn->stt  = stt;
     return FPA_OK;
+}
+
+static int nwave_host_collect(const PendingNwave& pn, int device) {
+    if (!pn.st) return FPA_OK;
+    FPA_TRY(use_device(device));
+    if (pn.tr) FPA_TRY(down(pn.user.A_trace, pn.tr, pn.n_tr * 8, pn.st));
+    if (pn.Ae) FPA_TRY(down(pn.user.A_end, pn.Ae, pn.B * pn.N * 16, pn.st));
+    if (pn.Pm) FPA_TRY(down(pn.user.Pmax, pn.Pm, pn.B * pn.N * 8, pn.st));
+    FPA_TRY(down(pn.user.status, pn.stt, pn.B * 4, pn.st));
+    return FPA_OK;
+}
+
+int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device) {
+    PendingNwave pn;
+    FPA_TRY(nwave_host_launch(d, device, &pn));
+    FPA_TRY(nwave_host_collect(pn, device));
+    if (pn.st) FPA_CUDA(cudaStreamSynchronize(pn.st));
+    return FPA_OK;
+}
+
+int fpa_nwave_rk4_batch_multi_host(const fpa_nwave_desc* d, int n_devices, const int* devices) {
+    FPA_TRY(nwave_host_check(d));
+    FPA_REQUIRE(n_devices >= 1 && n_devices <= 64 && devices != nullptr, "need 1..64 device ordinals");
+    if (n_devices == 1) return fpa_nwave_rk4_batch_host(d, devices[0]);
+    const int64_t ns = fpa_n_saved(d->n_steps, d->save_every), N = d->n_waves;
+    PendingNwave  pend[64];
+    return run_on_devices(
+        n_devices, devices, pend,
+        [&](int k, PendingNwave* pn) {
+            int64_t lo, hi;
+            balanced_range(d->n_points, n_devices, k, &lo, &hi);
+            *pn = PendingNwave();
+            if (hi <= lo) return (int)FPA_OK;
+            fpa_nwave_desc part = *d;
+            part.n_points = hi - lo;
+            part.beta     = d->beta + lo * d->beta_stride * N;
+            part.gamma    = d->gamma + lo * d->gamma_stride;
+            part.alpha    = d->alpha + lo * d->alpha_stride;
+            part.A0       = d->A0 + lo * d->A0_stride * N * 2;
+            if (d->A_trace) part.A_trace = d->A_trace + lo * ns * N * 2;
+            if (d->A_end) part.A_end = d->A_end + lo * N * 2;
+            if (d->Pmax) part.Pmax = d->Pmax + lo * N;
+            if (d->status) part.status = d->status + lo;
+            return nwave_host_launch(&part, devices[k], pn);
+        },
+        nwave_host_collect);
 }
 
 // ------------------------------------------------------------------ measurement helpers

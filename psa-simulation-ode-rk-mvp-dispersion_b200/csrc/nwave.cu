@@ -16,6 +16,7 @@
 // file as well; tests compare it bit-for-bit with the Python restatement in oracle/.
 #include "fpa_common.cuh"
 
+#include <math.h>
 #include <vector>
 
 namespace fpa {
@@ -357,6 +358,44 @@ extern "C" int64_t fpa_enumerate_triplets(int32_t N, const int32_t* g, fpa_tripl
                         if (count >= cap) {
                             fpa::set_error("fpa_enumerate_triplets: output capacity %lld too small",
                                            (long long)cap);
+                            return -1;
+                        }
+                        out[count].k = (int16_t)k;
+                        out[count].l = (int16_t)l;
+                        out[count].m = (int16_t)m;
+                        out[count].weight = (int16_t)(k == l ? 1 : 2);
+                    }
+                    ++count;
+                }
+            }
+        }
+    }
+    if (row_ptr) row_ptr[N] = count;
+    return count;
+}
+
+extern "C" int64_t fpa_enumerate_triplets_omega(int32_t N, const double* omega, double atol, double rtol, fpa_triplet* out,
+                                                int64_t cap, int64_t* row_ptr) {
+    if (N < 1 || N > 32767 || omega == nullptr || !(atol >= 0.0) || !(rtol >= 0.0)) {
+        fpa::set_error("fpa_enumerate_triplets_omega: need 1 <= N <= 32767, an omega array and non-negative tolerances");
+        return -1;
+    }
+    int64_t count = 0;
+    for (int32_t n = 0; n < N; ++n) {
+        if (row_ptr) row_ptr[n] = count;
+        for (int32_t k = 0; k < N; ++k) {
+            for (int32_t l = k; l < N; ++l) {
+                const volatile double lhs = omega[k] + omega[l];   // rounded to double, as numpy does
+                for (int32_t m = 0; m < N; ++m) {
+                    if (m == k || m == l) continue;
+                    const volatile double rhs = omega[m] + omega[n];
+                    // numpy.isclose for finite values: |a - b| <= atol + rtol * |b|
+                    const volatile double diff = lhs - rhs;
+                    const volatile double tol = rtol * fabs(rhs);
+                    if (!(fabs(diff) <= atol + tol)) continue;
+                    if (out) {
+                        if (count >= cap) {
+                            fpa::set_error("fpa_enumerate_triplets_omega: output capacity %lld too small", (long long)cap);
                             return -1;
                         }
                         out[count].k = (int16_t)k;

@@ -72,6 +72,20 @@ def uniform_comb_plan(omega_center: float, spacing: float, indices: Sequence[int
     return NWavePlan(omega=omega, grid_index=g, table=table, row_ptr=rows, labels=tuple(labels))
 
 
+def irregular_plan(omega: Sequence[float], *, atol: float = 0.0, rtol: float = 1e-12,
+                   labels: Sequence[str] = ()) -> NWavePlan:
+    """Plan for lines that do NOT sit on a uniform grid: the triplet table is enumerated by photon-energy
+    matching with the reference's tolerance rule (numpy.isclose(w_k + w_l, w_m + w_n, atol, rtol),
+    frequency_plan.py:112-131).  Such a plan always integrates through the enumerated-triplet kernel."""
+    w = np.ascontiguousarray(omega, dtype=float).reshape(-1)
+    if w.size == 0:
+        raise ValueError("omega must not be empty")
+    if np.any(w <= 0.0) or not np.all(np.isfinite(w)):
+        raise ValueError("omega must contain finite positive angular frequencies (rad/s)")
+    table, rows = _device.enumerate_triplets_omega(w, atol=atol, rtol=rtol)
+    return NWavePlan(omega=w, grid_index=np.full(w.size, -1, np.int32), table=table, row_ptr=rows, labels=tuple(labels))
+
+
 def four_wave_plan(omega: Sequence[float]) -> NWavePlan:
     """The reference's FIXED process table for [pump1, pump2, signal, idler]: one non-degenerate
     FWM term per wave, never enumerated from omega (a uniform 4-line grid would enumerate to 10
@@ -99,8 +113,7 @@ def _grid_or_none(plan: NWavePlan, form: str):
     (`auto` / `comb`); `table` or an off-grid plan uses the enumerated triplets."""
     if form not in ("auto", "comb", "table"):
         raise ValueError("form must be 'auto', 'comb' or 'table'")
-    off_grid = bool(np.all(plan.grid_index < 0)) and plan.grid_index.size > 1 and \
-        plan.grid_index.min() == plan.grid_index.max()
+    off_grid = bool(np.all(plan.grid_index < 0)) and plan.grid_index.min() == plan.grid_index.max()
     if form == "comb" and off_grid:
         raise ValueError("the convolution form needs an integer-grid plan")
     return None if (form == "table" or off_grid) else plan.grid_index
@@ -132,18 +145,19 @@ class NWaveRHS:
                                    self.plan.row_ptr, z0=z0, z_max=z_max, n_steps=n_steps,
                                    save_every=save_every, trace=trace, end=end, pmax=pmax,
                                    check_nan=check_nan, grid_index=_grid_or_none(self.plan, self.form),
-                                   force_table=self.form == "table")
+                                   force_table=self.form == "table", force_comb=self.form == "comb")
 
 
 def run_nwave_simulation(cfg: SimulationConfig, plan: NWavePlan, *, gamma, alpha, p_in=None,
                          phase_in=None, A0=None, dispersion: Optional[DispersionParams] = None,
                          beta=None, max_order: int = 4, length_unit: str = "m",
                          outputs: Sequence[str] = ("trace",), form: str = "auto",
-                         device: Optional[int] = None) -> dict:
+                         device: Optional[int] = None, devices=None) -> dict:
     """B >= 1 N-wave runs in one launch.  Initial state from p_in/phase_in [N] or A0 [B,N];
     gamma / alpha scalars or [B]; per-wave beta from `dispersion` (per length_unit) or given
-    explicitly ([N] or [B,N]).  `form`: 'auto' (convolution form for integer-grid plans, else the
-    triplet table), 'comb', 'table'.  Returns dict(z, A_trace[B,n_saved,N], A_end, Pmax, status)."""
+    explicitly ([N] or [B,N]).  `form`: 'auto' (the library picks: convolution form for integer-grid plans
+    within its limits unless they are sparse, else the triplet table), 'comb', 'table'.  `devices=[...]`
+    splits the points over several GPUs.  Returns dict(z, A_trace[B,n_saved,N], A_end, Pmax, status)."""
     validate_config(cfg)
     s = _length_scale_to_m(length_unit)
     N = plan.n_waves
@@ -166,8 +180,9 @@ def run_nwave_simulation(cfg: SimulationConfig, plan: NWavePlan, *, gamma, alpha
     r = _device.nwave_batch(beta, np.asarray(gamma, dtype=float) / s, np.asarray(alpha, dtype=float) / s,
                             A0.reshape(-1, N), plan.table, plan.row_ptr, z_max=z_max, n_steps=n_steps,
                             save_every=cfg.save_every, trace="trace" in want, end="end" in want,
-                            pmax="pmax" in want, check_nan=cfg.check_nan, device=device,
-                            grid_index=_grid_or_none(plan, form), force_table=form == "table")
+                            pmax="pmax" in want, check_nan=cfg.check_nan, device=device, devices=devices,
+                            grid_index=_grid_or_none(plan, form), force_table=form == "table",
+                            force_comb=form == "comb")
     grid = np.linspace(0.0, z_max, n_steps + 1)
     r["z"] = np.concatenate((grid[:1], grid[cfg.save_every::cfg.save_every])) / s
     r["n_steps"] = n_steps

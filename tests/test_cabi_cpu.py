@@ -58,6 +58,39 @@ def test_triplet_enumerator_bit_exact(fpa, nw_oracle):
     assert plan.n_triplets == 2760 and plan.n_pairs() == 227 and plan.flops_per_step() > 0
 
 
+def test_off_grid_triplet_enumerator_bit_exact(fpa, nw_oracle):
+    """`fpa_enumerate_triplets_omega`: photon-energy matching with the reference's tolerance rule
+    (numpy.isclose(w_k + w_l, w_m + w_n, atol 0, rtol 1e-12), frequency_plan.py:112-131) for plans that are not
+    on an integer grid; canonical order, bit-exact against the numpy restatement; on a uniform grid it must give
+    the integer enumeration."""
+    rng = np.random.default_rng(0)
+    w0, dw = 1.2e15, 6.28e11
+    cases = [w0 + dw * np.arange(-6, 7),
+             w0 + dw * np.array([-7.5, -3.0, -1.0, 0.0, 1.0, 2.5, 3.0, 6.5, 9.0]),
+             w0 + dw * np.arange(-4, 5) * (1 + 1e-13 * rng.normal(size=9)),          # jitter below the tolerance
+             w0 + dw * np.arange(-4, 5) * (1 + 1e-9 * rng.normal(size=9))]           # jitter above it
+    planted = np.sort(w0 + dw * rng.uniform(-10, 10, 12))
+    planted[5] = planted[2] + planted[8] - planted[3]
+    cases.append(planted)
+    sizes = []
+    for w in cases:
+        table, rows = fpa._device.enumerate_triplets_omega(w)
+        ref_t, ref_r = nw_oracle.enumerate_triplets_omega(w)
+        got = np.stack([table["k"], table["l"], table["m"], table["weight"]], axis=1) if table.size else np.zeros((0, 4), int)
+        assert rows.tolist() == ref_r and np.array_equal(got, np.array(ref_t, dtype=np.int64).reshape(-1, 4))
+        sizes.append(int(table.size))
+    grid_t, grid_r = fpa._device.enumerate_triplets(np.arange(-6, 7))
+    uni_t, uni_r = fpa._device.enumerate_triplets_omega(cases[0])
+    assert np.array_equal(grid_t, uni_t) and np.array_equal(grid_r, uni_r)
+    assert sizes[2] == fpa._device.enumerate_triplets(np.arange(-4, 5))[0].size and sizes[3] < sizes[2] and sizes[4] >= 4
+    loose, _ = fpa._device.enumerate_triplets_omega(cases[3], rtol=1e-6)
+    assert loose.size == sizes[2]
+    plan = fpa.nwave.irregular_plan(cases[1], labels=[f"w{j}" for j in range(9)])
+    assert plan.n_waves == 9 and plan.n_triplets == sizes[1] and (plan.grid_index == -1).all()
+    with pytest.raises(ValueError):
+        fpa.nwave.irregular_plan([1.0e15, -2.0])
+
+
 def test_no_cpu_fallback(fpa):
     """Without a device every compute call raises; with one this test is skipped."""
     if fpa._lib.device_count() > 0:

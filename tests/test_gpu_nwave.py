@@ -157,3 +157,76 @@ def test_comb_equals_table_on_odd_shapes(gpu, lines, batch):
     assert np.max(np.abs(t["Pmax"] - c["Pmax"])) < 1e-12 * scale ** 2
     assert (c["status"] == -1).all()
 
+
+
+def test_irregular_and_sparse_plans_run_through_the_table_kernel(gpu, nw_oracle):
+    """Plans the convolution form does not suit: (i) lines off any integer grid (tolerance-matched enumeration),
+    (ii) a sparse wide grid, span 801 > 512 -- with form='auto' both integrate through the enumerated-triplet
+    kernel (round 1 raised NotImplementedError for (ii)); an explicit form='comb' beyond the limits still raises."""
+    nw = gpu.nwave
+    w0, dw = 1.2125e15, 6.28e11
+    disp = gpu.dispersion.DispersionParams(w0, beta2=-2.6e-29, beta3=3.3e-41, beta4=-1.6e-55)
+    cfg = gpu.config.custom_simulation_config(z_max=20.0, dz=0.1, save_every=50)
+    # (i) off-grid: two pumps, a signal and its idler, plus lines that match nothing
+    om = w0 + dw * np.array([-5.0, 5.0, 1.3, -1.3, 2.77, -7.41])
+    plan = nw.irregular_plan(om)
+    assert plan.n_triplets > 0
+    beta = nw.beta_per_wave(plan, disp)
+    p_in = np.array([0.4, 0.4, 1e-4, 1e-4, 1e-5, 1e-5])
+    r = nw.run_nwave_simulation(cfg, plan, gamma=0.0115, alpha=1e-4, p_in=p_in, beta=beta, outputs=("trace", "end"))
+    table = [(int(a), int(b), int(c), int(d)) for a, b, c, d in zip(plan.table["k"], plan.table["l"], plan.table["m"],
+                                                                      plan.table["weight"])]
+    z_ref, A_ref = nw_oracle.march(np.sqrt(p_in).astype(complex), 0.0115, 1e-4, beta, table, plan.row_ptr.tolist(),
+                                   z_max=20.0, n_steps=200, save_every=50)
+    assert np.max(np.abs(r["A_trace"][0] - A_ref)) < 1e-12 * np.max(np.abs(A_ref))
+    with pytest.raises(ValueError):
+        nw.run_nwave_simulation(cfg, plan, gamma=0.0115, alpha=1e-4, p_in=p_in, beta=beta, form="comb")
+    # (ii) sparse wide grid
+    sparse = nw.uniform_comb_plan(w0, dw / 100.0, [-400, 0, 400])
+    bs = nw.beta_per_wave(sparse, disp)
+    p3 = np.array([1e-4, 0.5, 1e-4])
+    a = nw.run_nwave_simulation(cfg, sparse, gamma=0.0115, alpha=1e-4, p_in=p3, beta=bs, outputs=("end",))      # auto
+    b = nw.run_nwave_simulation(cfg, sparse, gamma=0.0115, alpha=1e-4, p_in=p3, beta=bs, outputs=("end",), form="table")
+    assert np.array_equal(a["A_end"], b["A_end"]) and (a["status"] == -1).all()
+    with pytest.raises(NotImplementedError):
+        nw.run_nwave_simulation(cfg, sparse, gamma=0.0115, alpha=1e-4, p_in=p3, beta=bs, outputs=("end",), form="comb")
+    # a moderately sparse grid inside the comb limits: 'auto' picks the table (span^2 > 5 T), both forms agree
+    mid = nw.uniform_comb_plan(w0, dw, [-40, -3, 0, 3, 40])
+    bm = nw.beta_per_wave(mid, disp)
+    p5 = np.array([1e-5, 0.3, 0.4, 1e-4, 1e-5])
+    t_ = nw.run_nwave_simulation(cfg, mid, gamma=0.0115, alpha=1e-4, p_in=p5, beta=bm, outputs=("end",), form="table")
+    c_ = nw.run_nwave_simulation(cfg, mid, gamma=0.0115, alpha=1e-4, p_in=p5, beta=bm, outputs=("end",), form="comb")
+    u_ = nw.run_nwave_simulation(cfg, mid, gamma=0.0115, alpha=1e-4, p_in=p5, beta=bm, outputs=("end",))
+    assert np.array_equal(u_["A_end"], t_["A_end"])
+    assert np.max(np.abs(c_["A_end"] - t_["A_end"])) < 1e-13 * np.max(np.abs(t_["A_end"]))
+
+
+def test_bad_grid_slots_are_rejected(gpu):
+    D = gpu._device
+    table, rows = D.enumerate_triplets([0, 1, 2])
+    A0 = np.ones((1, 3), dtype=complex)
+    with pytest.raises(ValueError, match="distinct"):
+        D.nwave_batch(np.zeros(3), 0.01, 0.0, A0, table, rows, z_max=1.0, n_steps=4, grid_index=[0, 1, 1])
+
+
+def test_multi_device_nwave_batch_equals_single_device(gpu):
+    """`fpa_nwave_rk4_batch_multi_host` (BASELINE config 5 shape: a batch of pump powers): contiguous balanced
+    point ranges over the listed devices (a one-GPU box repeats device 0); every shard uses the same kernel as the
+    whole batch here (CTA per point), so the results are bit-identical."""
+    nw = gpu.nwave
+    w0 = 2 * np.pi * 299792458.0 / 1550e-9
+    plan = nw.uniform_comb_plan(w0, 2 * np.pi * 100e9, range(-16, 16))
+    beta = nw.beta_per_wave(plan, gpu.dispersion.DispersionParams(omega_ref=w0, beta2=-2.57e-29, beta3=3.30e-41, beta4=-1.63e-55))
+    rng = np.random.default_rng(4)
+    B = 37
+    A0 = np.sqrt(rng.uniform(1e-6, 0.3, (B, 32))) * np.exp(1j * rng.uniform(0, 6.28, (B, 32)))
+    gam = rng.uniform(5e-3, 2e-2, B)
+    cfg = gpu.config.custom_simulation_config(z_max=30.0, dz=0.1, save_every=100)
+    n_dev = gpu._lib.device_count()
+    for form in ("comb", "table"):
+        one = nw.run_nwave_simulation(cfg, plan, gamma=gam, alpha=2e-4, A0=A0, beta=beta, outputs=("trace", "end", "pmax"), form=form)
+        for count in (2, 5):
+            many = nw.run_nwave_simulation(cfg, plan, gamma=gam, alpha=2e-4, A0=A0, beta=beta, outputs=("trace", "end", "pmax"),
+                                           form=form, devices=[k % n_dev for k in range(count)])
+            for k in ("A_trace", "A_end", "Pmax", "status"):
+                assert one[k].tobytes() == many[k].tobytes(), (k, form, count)
