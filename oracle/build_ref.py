@@ -92,9 +92,16 @@ def load() -> types.SimpleNamespace:
         raise ImportError("oracle/_ref is not built (run oracle/build_ref.py where /root/reference exists)")
     import importlib
 
-    if "matplotlib" not in sys.modules:
+    stubbed = "matplotlib" not in sys.modules
+    if stubbed:   # scan_mismtach / plotting import matplotlib for their figures; it is not installed here
+
+        def _plt_attr(attr):
+            if attr.startswith("__"):
+                raise AttributeError(attr)
+            return _Anything()
+
         mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
-        plt.__getattr__ = lambda attr: _Anything()  # type: ignore[attr-defined]
+        plt.__getattr__ = _plt_attr  # type: ignore[attr-defined]
         mpl.pyplot = plt
         sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
     saved = {m: sys.modules.pop(m) for m in MODULES if m in sys.modules}
@@ -109,6 +116,9 @@ def load() -> types.SimpleNamespace:
         for m in MODULES:
             sys.modules.pop(m, None)
         sys.modules.update(saved)
+        if stubbed:   # the reference modules keep their own reference to the stub; nobody else should see it
+            sys.modules.pop("matplotlib", None)
+            sys.modules.pop("matplotlib.pyplot", None)
     return types.SimpleNamespace(**mods)
 
 
