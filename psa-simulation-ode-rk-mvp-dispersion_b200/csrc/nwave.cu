@@ -106,18 +106,32 @@ __device__ double rhs_stage(const Smem& s, const NwaveParams& p, const fpa_tripl
     for (int n = warp; n < N; n += nwarps) {
         const int e0 = s.rows[n], e1 = s.rows[n + 1];
         double rr = 0.0, ri = 0.0;
-        for (int e = e0 + lane; e < e1; e += 32) {
-            const fpa_triplet t = table[e];
+        // one entry: D * At_k At_l conj(At_m)
+        auto term = [&](const fpa_triplet t, double& ar, double& ai) {
             const double kr = s.At[2 * t.k], ki = s.At[2 * t.k + 1];
             const double lr = s.At[2 * t.l], li = s.At[2 * t.l + 1];
             const double mr = s.At[2 * t.m], mi = s.At[2 * t.m + 1];
             const double w  = (double)t.weight;
             const double qr = w * fma(-ki, li, kr * lr);
             const double qi = w * fma(kr, li, ki * lr);
-            // q * conj(m)
-            rr = fma(qr, mr, fma(qi, mi, rr));
-            ri = fma(qi, mr, fma(-qr, mi, ri));
+            ar = fma(qr, mr, fma(qi, mi, ar));   // q * conj(m)
+            ai = fma(qi, mr, fma(-qr, mi, ai));
+        };
+        // A table that does not fit into shared memory streams from L2 (N = 64: 674 KB per RHS and scan point):
+        // four entries per lane are requested before the first one is used, and two accumulator pairs keep the
+        // FMA chains apart -- the rolled loop ran at the latency of one load per entry (~800 cycles).
+        double r2 = 0.0, i2 = 0.0;
+        int    e = e0 + lane;
+        for (; e + 96 < e1; e += 128) {
+            const fpa_triplet t0 = table[e], t1 = table[e + 32], t2 = table[e + 64], t3 = table[e + 96];
+            term(t0, rr, ri);
+            term(t1, r2, i2);
+            term(t2, rr, ri);
+            term(t3, r2, i2);
         }
+        for (; e < e1; e += 32) term(table[e], rr, ri);
+        rr += r2;
+        ri += i2;
         rr = warp_sum(rr);
         ri = warp_sum(ri);
         if (lane == 0) {
