@@ -437,10 +437,22 @@ __global__ void __launch_bounds__(kCombThreads, W == 1 ? 3 : 2) nwave_comb_kerne
 // =====================================================================================================
 constexpr int kSk8 = 3;
 
-// re + i*im += a * w
-__device__ __forceinline__ void cmac(double& re, double& im, const double2 a, const double2 w) {
-    re = fma(a.x, w.x, fma(-a.y, w.y, re));
-    im = fma(a.x, w.y, fma(a.y, w.x, im));
+// acc[t] += a * win[(k + t) & 7] for the 8 outputs of a tile, as two runs of 16 FMAs that share one operand
+// each (first a.y, then a.x): consecutive FP64 instructions with a common operand get it from the operand-reuse
+// cache and fetch two registers instead of three -- an FMA fetching three registers holds the pipe for 3 cycles
+// instead of 2 (tools/dfma_operand_probe.cu).  The two FMAs of one accumulator are 16 instructions apart.
+template <int K>
+__device__ __forceinline__ void term8(double (&re)[8], double (&im)[8], const double2 a, const double2 (&win)[8]) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        re[t] = fma(-a.y, win[(K + t) & 7].y, re[t]);
+        im[t] = fma(a.y, win[(K + t) & 7].x, im[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        re[t] = fma(a.x, win[(K + t) & 7].x, re[t]);
+        im[t] = fma(a.x, win[(K + t) & 7].y, im[t]);
+    }
 }
 
 // (a.x, +-a.y): conj(a) * w is computed as a' * w with the sign bit of a.y flipped after the load (an integer
@@ -466,16 +478,17 @@ __device__ __forceinline__ void roll8_mac(const double2* __restrict__ a, const d
     double2 av = load_a(ap, sign_flip);
     for (int i = i0; i < i1; i += 8) {
         wp += 9;  // the next 8 words of w (one spare word in between)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            // operands of the next term are requested before this term's 32 FMAs
-            const double2 nw = wp[k];
-            const double2 an = load_a(ap + (k < 7 ? k + 1 : 9), sign_flip);   // k == 7: first word of the next group
-#pragma unroll
-            for (int t = 0; t < 8; ++t) cmac(re[t], im[t], av, win[(k + t) & 7]);
-            win[k] = nw;
-            av = an;
+        // operands of the next term are requested before this term's 32 FMAs
+#define FPA_TERM(K)                                                                     \
+        {                                                                               \
+            const double2 nw = wp[K];                                                   \
+            const double2 an = load_a(ap + (K < 7 ? K + 1 : 9), sign_flip);             \
+            term8<K>(re, im, av, win);                                                  \
+            win[K] = nw;                                                                \
+            av = an;                                                                    \
         }
+        FPA_TERM(0) FPA_TERM(1) FPA_TERM(2) FPA_TERM(3) FPA_TERM(4) FPA_TERM(5) FPA_TERM(6) FPA_TERM(7)
+#undef FPA_TERM
         ap += 9;
     }
 }
@@ -488,15 +501,16 @@ __device__ __forceinline__ void roll4_mac(const double2* __restrict__ a, const d
     for (int t = 0; t < 8; ++t) win[t] = w[padx<kSk8>(obase + i0 + t)];
     const double2* ap = a + padx<kSk8>(i0);                  // 4 words, no pad inside (i0 % 4 == 0)
     const double2* wp = w + padx<kSk8>(obase + i0 + 8);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double2 av = load_a(ap + k, sign_flip);
-        double2       nw = make_double2(0.0, 0.0);
-        if (k < 3) nw = wp[k];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) cmac(re[t], im[t], av, win[(k + t) & 7]);
-        win[k] = nw;
+#define FPA_TERM4(K)                                                                    \
+    {                                                                                   \
+        const double2 av = load_a(ap + K, sign_flip);                                   \
+        double2       nw = make_double2(0.0, 0.0);                                      \
+        if (K < 3) nw = wp[K];                                                          \
+        term8<K>(re, im, av, win);                                                      \
+        win[K] = nw;                                                                    \
     }
+    FPA_TERM4(0) FPA_TERM4(1) FPA_TERM4(2) FPA_TERM4(3)
+#undef FPA_TERM4
 }
 
 // One level of the reduce-scatter over the parts: lanes d apart exchange HALF of the CNT values they hold
@@ -652,54 +666,76 @@ struct CombStep {
     double gamma, nha, hh, h, h6, h3;
 };
 
-template <int S>
-__device__ __forceinline__ void wave_pass(const CombSmem& s, int j, int slot_pad, const CombStep& k, bool resync_next,
-                                          double z_next, bool check, int& nf) {
-    const double2 r = s.R[slot_pad];
-    const double2 e = S == 0 ? s.E[j] : s.Eh[j];
-    const double2 x = s.ys[j];
-    const double  fr = fma(r.y, e.y, r.x * e.x);
-    const double  fi = fma(r.y, e.x, -(r.x * e.y));
-    const double  kr = fma(k.nha, x.x, -(k.gamma * fi));
-    const double  ki = fma(k.nha, x.y, k.gamma * fr);
-    const double  wa = (S == 0 || S == 3) ? k.h6 : k.h3;
-    const double2 acc = s.yn[j];
-    double2       ysn, en;
-    if (S == 3) {
-        ysn = make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y));    // the step's result
-        s.y[j] = ysn;
-        s.yn[j] = ysn;
-        if (check && (nonfinite(ysn.x) || nonfinite(ysn.y))) nf = 1;
-        if (resync_next) {   // exact phase every kCombResync steps
-            double sn, cs;
-            sincos(s.beta[j] * z_next, &sn, &cs);
-            en = make_double2(cs, sn);
-        } else {
-            en = e;          // stage 3 ran at z + h: that is the next step's starting phase
-        }
-        s.E[j] = en;
-    } else {
-        const double  wb = S == 2 ? k.h : k.hh;
-        const double2 y0 = s.y[j];
-        s.yn[j] = make_double2(fma(wa, kr, acc.x), fma(wa, ki, acc.y));
-        ysn = make_double2(fma(wb, kr, y0.x), fma(wb, ki, y0.y));
-        if (S == 1) {
-            en = e;          // stages 1 and 2 share the abscissa z + h/2
-        } else {             // S = 0 -> z + h/2 ; S = 2 -> z + h
-            const double2 rot = s.rot[j];
-            en = make_double2(fma(-e.y, rot.y, e.x * rot.x), fma(e.x, rot.y, e.y * rot.x));
-            s.Eh[j] = en;
-            if (S == 2) s.E[j] = en;
-        }
+template <int S, int K>
+__device__ __forceinline__ void wave_pass(const CombSmem& s, const int (&j)[K], const int (&slot_pad)[K], const CombStep& k,
+                                          bool resync_next, double z_next, bool check, int& nf) {
+    // all loads of the K waves first, then K independent chains: a lane's waves overlap their latencies
+    double2 r[K], e[K], x[K], acc[K], y0[K], rot[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        r[q]   = s.R[slot_pad[q]];
+        e[q]   = S == 0 ? s.E[j[q]] : s.Eh[j[q]];
+        x[q]   = s.ys[j[q]];
+        acc[q] = s.yn[j[q]];
+        if (S != 3) y0[q] = s.y[j[q]];
+        if (S == 0 || S == 2) rot[q] = s.rot[j[q]];
     }
-    s.ys[j] = ysn;
-    s.At[slot_pad] = make_double2(fma(-ysn.y, en.y, ysn.x * en.x), fma(ysn.x, en.y, ysn.y * en.x));
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        const double fr = fma(r[q].y, e[q].y, r[q].x * e[q].x);
+        const double fi = fma(r[q].y, e[q].x, -(r[q].x * e[q].y));
+        const double kr = fma(k.nha, x[q].x, -(k.gamma * fi));
+        const double ki = fma(k.nha, x[q].y, k.gamma * fr);
+        const double wa = (S == 0 || S == 3) ? k.h6 : k.h3;
+        double2      ysn, en;
+        if (S == 3) {
+            ysn = make_double2(fma(wa, kr, acc[q].x), fma(wa, ki, acc[q].y));    // the step's result
+            s.y[j[q]] = ysn;
+            s.yn[j[q]] = ysn;
+            if (check && (nonfinite(ysn.x) || nonfinite(ysn.y))) nf = 1;
+            if (resync_next) {   // exact phase every kCombResync steps
+                double sn, cs;
+                sincos(s.beta[j[q]] * z_next, &sn, &cs);
+                en = make_double2(cs, sn);
+            } else {
+                en = e[q];       // stage 3 ran at z + h: that is the next step's starting phase
+            }
+            s.E[j[q]] = en;
+        } else {
+            const double wb = S == 2 ? k.h : k.hh;
+            s.yn[j[q]] = make_double2(fma(wa, kr, acc[q].x), fma(wa, ki, acc[q].y));
+            ysn = make_double2(fma(wb, kr, y0[q].x), fma(wb, ki, y0[q].y));
+            if (S == 1) {
+                en = e[q];       // stages 1 and 2 share the abscissa z + h/2
+            } else {             // S = 0 -> z + h/2 ; S = 2 -> z + h
+                en = make_double2(fma(-e[q].y, rot[q].y, e[q].x * rot[q].x), fma(e[q].x, rot[q].y, e[q].y * rot[q].x));
+                s.Eh[j[q]] = en;
+                if (S == 2) s.E[j[q]] = en;
+            }
+        }
+        s.ys[j[q]] = ysn;
+        s.At[slot_pad[q]] = make_double2(fma(-ysn.y, en.y, ysn.x * en.x), fma(ysn.x, en.y, ysn.y * en.x));
+    }
 }
 
-// L lanes per scan point, 32 / L points per warp (all of them in lock-step: N, M and the step count are the
-// same for the whole batch).  L = 32 for batches that would otherwise leave sub-partitions without a warp;
-// L = 16 halves the shared-memory and shuffle operations per FMA (each lane runs twice as many terms per
-// window and per reduction) and is used once the batch still gives every sub-partition its warps.
+// The waves a lane owns (gl, gl + LW, ...; at most OWN of them) in pairs, so that two chains share one
+// straight-line region; a lane of the last, partly filled round handles its single wave alone.
+template <int S, int OWN, int LW>
+__device__ __forceinline__ void wave_passes(const CombSmem& s, int gl, int N, const int (&slot_pad)[OWN], const CombStep& k,
+                                            bool resync_next, double z_next, bool check, int& nf) {
+#pragma unroll
+    for (int q = 0; q < OWN; q += 2) {
+        const int j0 = gl + q * LW, j1 = j0 + LW;
+        if (OWN - q >= 2 && j1 < N) {
+            const int jj[2] = {j0, j1}, sp[2] = {slot_pad[q], slot_pad[q + 1 < OWN ? q + 1 : q]};
+            wave_pass<S, 2>(s, jj, sp, k, resync_next, z_next, check, nf);
+        } else if (j0 < N) {
+            const int jj[1] = {j0}, sp[1] = {slot_pad[q]};
+            wave_pass<S, 1>(s, jj, sp, k, resync_next, z_next, check, nf);
+        }
+    }
+}
+
 // Barrier over the W warps of one scan point (W = 1: the warp itself).  Named barriers 1..8 of the CTA.
 template <int W>
 __device__ __forceinline__ void point_sync(int point_in_cta) {
@@ -821,26 +857,10 @@ __global__ void __launch_bounds__(kCombThreads, L == 32 ? 2 : 1) nwave_comb8_ker
             // ---- k, RK4 bookkeeping and the next stage's phases / rotated state: one pass per wave, straight-line
             // code per stage (one uniform jump instead of a chain of stage tests)
             switch (stage) {
-            case 0:
-#pragma unroll
-                for (int q = 0; q < kOwn; ++q)
-                    if (gl + q * LW < N) wave_pass<0>(s, gl + q * LW, slot_pad[q], ks, false, 0.0, false, nf);
-                break;
-            case 1:
-#pragma unroll
-                for (int q = 0; q < kOwn; ++q)
-                    if (gl + q * LW < N) wave_pass<1>(s, gl + q * LW, slot_pad[q], ks, false, 0.0, false, nf);
-                break;
-            case 2:
-#pragma unroll
-                for (int q = 0; q < kOwn; ++q)
-                    if (gl + q * LW < N) wave_pass<2>(s, gl + q * LW, slot_pad[q], ks, false, 0.0, false, nf);
-                break;
-            default:
-#pragma unroll
-                for (int q = 0; q < kOwn; ++q)
-                    if (gl + q * LW < N) wave_pass<3>(s, gl + q * LW, slot_pad[q], ks, resync_next, z_next, p.check != 0, nf);
-                break;
+            case 0: wave_passes<0, kOwn, LW>(s, gl, N, slot_pad, ks, false, 0.0, false, nf); break;
+            case 1: wave_passes<1, kOwn, LW>(s, gl, N, slot_pad, ks, false, 0.0, false, nf); break;
+            case 2: wave_passes<2, kOwn, LW>(s, gl, N, slot_pad, ks, false, 0.0, false, nf); break;
+            default: wave_passes<3, kOwn, LW>(s, gl, N, slot_pad, ks, resync_next, z_next, p.check != 0, nf); break;
             }
             if (W > 1 && stage == 3 && nf) nf_flag[i & 1] = 1;
             FPA_TICK8(3);
