@@ -406,9 +406,9 @@ def run_ours(args) -> None:
     achieved_tf = FLOPS_PER_POINT_STEP * B * n_steps / (kernel_ms * 1e-3) / 1e12
     gain_dev = sweep.t_gain.cpu().numpy()
     if world > 1:       # every rank holds the gathered map; rank 0 later checks it against the assembled host map
-        parts = t_all.view(world, tall).cpu().numpy()
+        shards = t_all.view(world, tall).cpu().numpy()
         sizes = [balanced_range(total_points, world, r) for r in range(world)]
-        full_dev = np.concatenate([parts[r, :b - a] for r, (a, b) in enumerate(sizes)])
+        full_dev = np.concatenate([shards[r, :b - a] for r, (a, b) in enumerate(sizes)])
     else:
         full_dev = gain_dev
 
