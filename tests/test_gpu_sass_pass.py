@@ -83,3 +83,28 @@ def test_exact_phase_kernel_bit_identical(gpu, grid):
             outputs=("end", "pmax", "trace"), phase_exact=True)
     a, b = _both(gpu, run)
     _same(a, b)
+
+
+def test_segment_scheduler_kernels_bit_identical(gpu, golden):
+    """The persistent (z-segment scheduler) instantiations go through the pass too; they only run for batches of
+    one wave of the resident warps or more, so they need their own comparison with the ptxas-schedule build:
+    the fused sweep (lossy and lossless) and the batch integrator in every output mode."""
+    b2, b3, b4, wref = golden["b4_beta"]
+    disp = gpu.dispersion.DispersionParams(omega_ref=wref, beta2=b2, beta3=b3, beta4=b4)
+    cfg = gpu.config.custom_simulation_config(z_max=40.0, dz=0.2, save_every=7)
+    lam1 = np.linspace(1545e-9, 1555e-9, 90)
+    lam3 = np.linspace(1540e-9, 1565e-9, 1000)          # 90 000 points = 1.19 waves
+    for alpha in (0.0, 1.15e-4):
+        run = lambda: gpu.scan_mismtach.sweep_gain_2d(  # noqa: E731
+            cfg=cfg, lambda_p1_m=lam1, lambda_signal_m=lam3, lambda_p2_m=1558e-9, gamma=11.5e-3, alpha=alpha,
+            p_in=golden["b4_p_in"], dispersion=disp, gain_unit="linear", want_pmax=True)
+        a, b = _both(gpu, run)
+        _same(a, b)
+    db = np.linspace(-40.0, 40.0, 80_000)
+    cfg3 = gpu.config.custom_simulation_config(z_max=0.13, dz=1e-3, save_every=10)
+    for outputs in (("end", "pmax"), ("trace",), ("end",), ("trace", "end", "pmax")):
+        for alpha in (0.0, 0.2):
+            run = lambda: gpu.simulation.run_batch_simulation(      # noqa: E731
+                cfg3, gamma=10.0, alpha=alpha, delta_beta=db, p_in=[0.1, 0.1, 1e-5, 0.0], length_unit="km", outputs=outputs)
+            a, b = _both(gpu, run)
+            _same(a, b)

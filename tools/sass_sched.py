@@ -756,10 +756,15 @@ def schedule_block(seq, tries=60, seed=1, stall_cost=0.05, w_over=None, polish=T
             w["noise"] = 0.0
         if w_over:
             w.update(w_over)
-        res = bs.run(rng, w)
+        try:
+            res = bs.run(rng, w)
+        except ValueError:      # this greedy run painted itself into a corner (a gap above the stall limit): next one
+            continue
         key = (res[0] + stall_cost * res[1],)
         if best is None or key < best[0]:
             best = (key, res)
+    if best is None:
+        raise ValueError("no encodable schedule found (stall count above the limit in every attempt)")
     if beam_width:
         res = bs.beam_search(width=beam_width, stall_cost=stall_cost)
         if res is not None:
@@ -907,6 +912,14 @@ def patch_function(ins, mode, tries, log, stall_cost=0.05, w_over=None, kept=Non
         m0 += th
         if mode == "sched":
             try:
+                # Safety envelope: blocks with memory loads (LDS / LDG / LDL / LD) keep ptxas' order.  The pass was
+                # validated -- symbolically here, bit for bit on the GPU against the ptxas-schedule build -- on the RK4
+                # hot blocks, whose only variable-latency instructions are constant-bank loads, I2F and MUFU of the
+                # phase re-synchronisation.  The N-wave comb kernel's blocks refill their rolling register windows
+                # from shared memory in the middle of the arithmetic that still reads them; re-ordered, they passed
+                # the symbolic check and computed DIFFERENT values on the GPU (round-2 experiment).
+                if any(x_.base in ("LDS", "LDG", "LDL", "LD", "LDSM") for x_ in seq):
+                    raise ValueError("block holds memory loads: outside the validated envelope of the pass")
                 new, st = schedule_block(seq, tries=tries, stall_cost=stall_cost, w_over=w_over, beam_width=48)
                 verify_block(seq, new)
             except (ValueError, SassVerifyError) as e:  # keep ptxas' block rather than risk it
