@@ -54,7 +54,7 @@ P_IN = [0.1, 0.1, 1e-7, 1e-7]
 LAM_P2 = 1558e-9
 FLOPS_PER_POINT_STEP = 568.0
 FLOPS_LOSSLESS = 504.0       # alpha == 0: the 4 x 8 loss FMAs of a step are not executed, so not credited
-FLUSH_BYTES = 160 << 20      # > 126 MB L2, written between steps
+FLUSH_BYTES = 136 << 20      # 142.6e6 B > the 126 MB L2, written between steps
 RESULT_OUT = sys.stdout      # main() replaces it with a private duplicate of the original stdout
 WORKLOAD = ("sweep2d_1000x1000_x2500steps (BASELINE configs[3]: pump x signal wavelength sweep, 1e6 scan points, "
             "z_max=500 m, dz=0.2 m, save_every=10, SYMMETRIC_EVEN(2,4) dbeta, max-over-saved signal gain)")
@@ -245,11 +245,51 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm helpers
+class PeerMaps:
+    """One full-size gain map per GPU of the box, each opened in every rank (CUDA IPC through the C ABI): the
+    sweep kernel stores each point's gain into all of them (`fpa_sweep_desc.peer_gain`), which IS the final
+    gather -- no collective after the kernel."""
+
+    def __init__(self, fpa, dist, torch, world, rank, local, n_points):
+        L, lib = fpa._lib, fpa._lib.lib()
+        self.L, self.lib, self.rank, self.n = L, lib, rank, n_points
+        self.own = C.c_void_p()
+        L.check(lib.fpa_dev_alloc(C.byref(self.own), n_points * 8, local))
+        handle = (C.c_char * 64)()
+        L.check(lib.fpa_ipc_export(self.own, handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        self.ptrs, self.opened = [], []
+        for r in range(world):
+            if r == rank:
+                self.ptrs.append(self.own.value)
+                continue
+            q = C.c_void_p()
+            L.check(lib.fpa_ipc_open(handles[r], C.byref(q)))
+            self.ptrs.append(q.value)
+            self.opened.append(q)
+        self.torch, self.dev = torch, torch.device("cuda", local)
+
+    def own_map(self):
+        """This rank's map as a torch tensor (no copy)."""
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.n,), "typestr": "<f8", "data": (self.own.value, False), "version": 3}
+        return self.torch.as_tensor(v, device=self.dev)
+
+    def close(self, dist):
+        for q in self.opened:
+            self.lib.fpa_ipc_close(q)
+        dist.barrier()              # nobody still has this rank's map open
+        self.lib.fpa_dev_free(self.own)
+
+
 class DeviceSweep:
     """Device-resident descriptor of one rank's share of a sweep: points [first, first + count) of the
     flattened rows x 1000 grid; the wavelength axes already live in HBM."""
 
-    def __init__(self, fpa, torch, dev, rows, first, count, disp, pm_cfg):
+    def __init__(self, fpa, torch, dev, rows, first, count, disp, pm_cfg, peer_maps=None):
         L, lib = fpa._lib, fpa._lib.lib()
         lam1, lam3 = grid_axes(rows)
         self.count = count
@@ -277,6 +317,10 @@ class DeviceSweep:
         d.gain_lin, d.status, d.Pmax, d.A_end = self.t_gain.data_ptr(), self.t_status.data_ptr(), None, None
         if not (first == 0 and count == rows * N3):
             d.first_point, d.n_sub_points = first, count
+        if peer_maps:       # the kernel stores every gain into the full-size map of every GPU of the box as well
+            d.n_peers = len(peer_maps)
+            for r, ptr in enumerate(peer_maps):
+                d.peer_gain[r] = ptr
         self.desc, self.L, self.lib = d, L, lib
 
     def launch(self, stream):
@@ -383,7 +427,22 @@ def run_ours(args) -> None:
     lo, hi = balanced_range(total_points, world, rank)
     if args.shard_of > 1:       # profiling aid: rank 0's share of an N-way split, on this one GPU
         lo, hi = balanced_range(total_points, args.shard_of, 0)
-    sweep = DeviceSweep(fpa, torch, dev, N1, lo, hi - lo, disp, pm_cfg)
+    # the final gather: peer stores by the sweep kernel itself (default), or an NCCL all-gather after it
+    peers, gather_how = None, "none (one GPU)"
+    if world > 1:
+        ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        if args.gather == "peer":
+            try:
+                peers = PeerMaps(fpa, dist, torch, world, rank, local, total_points)
+                ok += 1
+            except Exception as exc:          # noqa: BLE001 -- no peer access / IPC on this box: NCCL instead
+                print(f"rank {rank}: peer maps unavailable ({exc!r}); falling back to the NCCL all-gather", file=sys.stderr)
+        dist.all_reduce(ok)                   # all ranks or none
+        if peers is not None and int(ok.item()) != world:
+            peers = None
+        gather_how = ("kernel: NVLink peer stores into the full-size map of every GPU (fpa_sweep_desc.peer_gain)"
+                      if peers is not None else "NCCL all_gather_into_tensor after the kernel")
+    sweep = DeviceSweep(fpa, torch, dev, N1, lo, hi - lo, disp, pm_cfg, peer_maps=peers.ptrs if peers else None)
     B = hi - lo
     even = total_points % world == 0
     tall = -(-total_points // world)
@@ -391,7 +450,7 @@ def run_ours(args) -> None:
     t_pad = torch.zeros(tall, dtype=torch.float64, device=dev) if (world > 1 and not even) else None
 
     def gather_strong():
-        if world == 1:
+        if world == 1 or peers is not None:
             return
         if even:
             dist.all_gather_into_tensor(t_all, sweep.t_gain)               # the final result gather
@@ -406,9 +465,20 @@ def run_ours(args) -> None:
     achieved_tf = FLOPS_PER_POINT_STEP * B * n_steps / (kernel_ms * 1e-3) / 1e12
     gain_dev = sweep.t_gain.cpu().numpy()
     if world > 1:       # every rank holds the gathered map; rank 0 later checks it against the assembled host map
+        if peers is not None:   # untimed NCCL gather of the same results: the kernel-built map must equal it bit for bit
+            if even:
+                dist.all_gather_into_tensor(t_all, sweep.t_gain)
+            else:
+                t_pad[:B] = sweep.t_gain
+                dist.all_gather_into_tensor(t_all, t_pad)
+            torch.cuda.synchronize()
         shards = t_all.view(world, tall).cpu().numpy()
         sizes = [balanced_range(total_points, world, r) for r in range(world)]
         full_dev = np.concatenate([shards[r, :b - a] for r, (a, b) in enumerate(sizes)])
+        if peers is not None:
+            built = peers.own_map().cpu().numpy()
+            assert built.tobytes() == full_dev.tobytes(), f"rank {rank}: the map built by peer stores differs from the NCCL gather"
+            peers.close(dist)
     else:
         full_dev = gain_dev
 
@@ -554,7 +624,7 @@ def run_ours(args) -> None:
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD + (f" -- ONLY the first of {args.shard_of} shards (profiling aid)" if args.shard_of > 1 else ""),
                    "points_total": total_points, "points_per_gpu": B, "rk4_steps": n_steps,
-                   "parallelism": f"flattened point range split x{world}, final all-gather of the gain map" if world > 1 else "one GPU",
+                   "parallelism": f"flattened point range split x{world}; final gather: {gather_how}" if world > 1 else "one GPU",
                    "l2": f"{FLUSH_BYTES >> 20} MiB buffer written between steps (inside the timed region); "
                          "the kernel keeps its state in registers"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -786,6 +856,9 @@ def main() -> None:
     ap.add_argument("--scaling", default="both", choices=["both", "strong", "weak"],
                     help="N > 1: the headline is always strong scaling (the fixed 1e6-point grid split over the ranks); "
                          "'both' (default) and 'weak' also time 1e6 points per GPU and report it under \"weak\"")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the gain map is gathered -- by the sweep kernel (peer stores over NVLink, default) "
+                         "or by an NCCL all-gather after it")
     ap.add_argument("--no-cpu-baseline", action="store_true",
                     help="skip the CPU leg (profiling runs under ncu)")
     ap.add_argument("--shard-of", type=int, default=1,

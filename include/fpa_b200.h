@@ -223,7 +223,14 @@ typedef struct fpa_sweep_desc {
     int64_t       n_sub_points;  /*   [first_point, first_point + n_sub_points); 0, 0 = all.
                                     Every output array is then indexed by b - first_point
                                     (pass base + first_point to fill one full-size array).  */
+    int32_t       n_peers;       /* _dev entry, 0..FPA_MAX_PEERS: the kernel ALSO stores each point's gain   */
+    int32_t       reserved3;     /*   into peer_gain[p][b] (b = index in the WHOLE grid) for every p -- full-  */
+    double*       peer_gain[8];  /*   size gain maps in the memory of the GPUs of the box (this one included),
+                                    opened with fpa_ipc_open: the final result gather of a multi-GPU sweep
+                                     done by the sweep kernel itself over NVLink peer stores while
+                                    the other points still integrate -- no collective after the kernel.      */
 } fpa_sweep_desc;
+#define FPA_MAX_PEERS 8
 
 int fpa_yaman4_sweep_host(const fpa_sweep_desc* d, int device);
 /* The same sweep on several devices of one box from ONE process (scan points are
@@ -332,6 +339,15 @@ double fpa_yaman4_flops_per_step(void);
 /* Pinned host memory for the e2e path. */
 int fpa_host_alloc(void** ptr, int64_t bytes);
 int fpa_host_free(void* ptr);
+/* Device memory that can be shared with the other processes of the box (one rank per GPU): allocate on
+ * `device`, export a 64-byte handle, open it in the peer process (device pointer valid on the opener's current
+ * device; peer access is enabled by the open), close before the owner frees.  Used for the peer_gain maps above. */
+int fpa_dev_alloc(void** ptr, int64_t bytes, int device);
+int fpa_dev_free(void* ptr);
+int fpa_ipc_export(const void* dev_ptr, void* handle64);
+int fpa_ipc_open(const void* handle64, void** dev_ptr);
+int fpa_ipc_close(void* dev_ptr);
+
 /* Page-lock memory the caller already owns (e.g. a POSIX shared-memory segment several processes
  * map: every rank registers it and its kernels store their shard of the result straight into the
  * one host array).  Registered memory counts as pinned for every *_host entry point. */

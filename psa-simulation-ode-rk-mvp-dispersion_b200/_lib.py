@@ -71,6 +71,7 @@ class SweepDesc(C.Structure):
         ("gain_lin", C.c_void_p), ("Pmax", C.c_void_p), ("A_end", C.c_void_p),
         ("status", C.c_void_p),
         ("first_point", C.c_int64), ("n_sub_points", C.c_int64),
+        ("n_peers", C.c_int32), ("reserved3", C.c_int32), ("peer_gain", C.c_void_p * 8),
     ]
 
 
@@ -134,6 +135,11 @@ SIGNATURES = {
     "fpa_yaman4_flops_per_step": (C.c_double, []),
     "fpa_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "fpa_host_free": (C.c_int, [C.c_void_p]),
+    "fpa_dev_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int]),
+    "fpa_dev_free": (C.c_int, [C.c_void_p]),
+    "fpa_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fpa_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fpa_ipc_close": (C.c_int, [C.c_void_p]),
     "fpa_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
     "fpa_host_unregister": (C.c_int, [C.c_void_p]),
 }

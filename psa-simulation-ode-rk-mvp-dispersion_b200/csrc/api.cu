@@ -609,6 +609,7 @@ static int sweep_host_launch(const fpa_sweep_desc* d, int device, PendingSweep* 
     double*  m_Pm   = mapped(d->Pmax);
     double*  m_Ae   = mapped(d->A_end);
     fpa_sweep_desc dd = *d;
+    dd.n_peers      = 0;   // peer maps are device pointers: a feature of the _dev entry
     dd.plan.lambda1 = l1;
     dd.plan.lambda2 = l2;
     dd.plan.lambda3 = l3;
@@ -915,6 +916,42 @@ int fpa_host_alloc(void** ptr, int64_t bytes) {
 int fpa_host_free(void* ptr) {
     if (ptr == nullptr) return FPA_OK;
     FPA_CUDA(cudaFreeHost(ptr));
+    return FPA_OK;
+}
+
+int fpa_dev_alloc(void** ptr, int64_t bytes, int device) {
+    FPA_REQUIRE(ptr != nullptr && bytes > 0, "bad arguments");
+    FPA_TRY(use_device(device));
+    FPA_CUDA(cudaMalloc(ptr, (size_t)bytes));
+    return FPA_OK;
+}
+
+int fpa_dev_free(void* ptr) {
+    if (ptr == nullptr) return FPA_OK;
+    FPA_CUDA(cudaFree(ptr));
+    return FPA_OK;
+}
+
+int fpa_ipc_export(const void* dev_ptr, void* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI documents a 64-byte handle");
+    FPA_REQUIRE(dev_ptr != nullptr && handle64 != nullptr, "bad arguments");
+    cudaIpcMemHandle_t h;
+    FPA_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle64, &h, sizeof(h));
+    return FPA_OK;
+}
+
+int fpa_ipc_open(const void* handle64, void** dev_ptr) {
+    FPA_REQUIRE(dev_ptr != nullptr && handle64 != nullptr, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    FPA_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FPA_OK;
+}
+
+int fpa_ipc_close(void* dev_ptr) {
+    if (dev_ptr == nullptr) return FPA_OK;
+    FPA_CUDA(cudaIpcCloseMemHandle(dev_ptr));
     return FPA_OK;
 }
 

@@ -437,7 +437,21 @@ struct SweepExtra {
     double     p_signal;
     double*    gain_lin;    // [B]
     int64_t    first_point; // grid index of point 0 of this launch (sub-range sweeps; outputs are indexed locally)
+    double*    peer[FPA_MAX_PEERS];  // full-size gain maps on the GPUs of the box (peer memory), indexed by the grid
+    int        n_peers;
 };
+
+// The final gather of a multi-GPU sweep, fused into the kernel: the thread that finishes a point stores its gain
+// into the full-size map of every GPU of the box (NVLink peer stores, posted, 8 B per point and peer) while the
+// other points still integrate.
+__device__ __forceinline__ void store_gain(const SweepExtra& x, int64_t b, double gain) {
+    x.gain_lin[b] = gain;
+    if (x.n_peers > 0) {
+        const int64_t bg = b + x.first_point;
+        for (int q = 0; q < x.n_peers; ++q) x.peer[q][bg] = gain;
+        __threadfence_system();
+    }
+}
 
 // Prologue of one scan point: frequency plan, validity, reported and integration Delta-beta; writes the
 // plan outputs.  Returns false for points the reference's per-point try/except turns into NaN.
@@ -471,7 +485,7 @@ __device__ __forceinline__ void sweep_invalid(const Yaman4Params& p, const Sweep
     if (p.Pmax)
         for (int j = 0; j < 4; ++j) p.Pmax[b * 4 + j] = qn;
     if (p.status) p.status[b] = p.check ? 0 : FPA_POINT_OK;
-    x.gain_lin[b] = qn;
+    store_gain(x, b, qn);
 }
 
 // Epilogue of an integrated point: status, optional end state / maxima, and the sweep's gain metric.
@@ -499,7 +513,7 @@ __device__ __forceinline__ void sweep_epilogue(const Yaman4Params& p, const Swee
         const double q = pm[2] / x.p_signal;
         if (!nonfinite(q) && q > 0.0) gain = q;
     }
-    x.gain_lin[b] = gain;
+    store_gain(x, b, gain);
 }
 
 template <bool LOSS, int THREADS, int MIN_BLOCKS>
@@ -887,6 +901,12 @@ int yaman4_sweep_launch(const fpa_sweep_desc* d, void* scratch, int64_t scratch_
     x.p_signal = d->p_signal;
     x.gain_lin = d->gain_lin;
     x.first_point = d->first_point;
+    FPA_REQUIRE(d->n_peers >= 0 && d->n_peers <= FPA_MAX_PEERS, "n_peers must be in [0, %d]", FPA_MAX_PEERS);
+    x.n_peers = d->n_peers;
+    for (int q = 0; q < FPA_MAX_PEERS; ++q) {
+        x.peer[q] = q < d->n_peers ? d->peer_gain[q] : nullptr;
+        FPA_REQUIRE(q >= d->n_peers || x.peer[q] != nullptr, "peer_gain[%d] is NULL", q);
+    }
 
     Yaman4Params p;
     memset(&p, 0, sizeof(p));

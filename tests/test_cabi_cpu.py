@@ -32,7 +32,7 @@ def test_struct_layouts_match_header(fpa):
     # sizes computed by hand from the header (LP64): catches a drifted field
     assert C.sizeof(L.Yaman4Desc) == 8 * 8 + 2 * 8 + 2 * 8 + 8 + 8 + 4 * 8 + 2 * 8 + 2 * 8
     assert C.sizeof(L.PlanDesc) == 2 * 8 + 4 * 8 + 3 * 4 + 12 * 4 + 4 + 13 * 8 + 4 * 8 + 3 * 8
-    assert C.sizeof(L.SweepDesc) == C.sizeof(L.PlanDesc) + 8 * 8 + 6 * 8 + 8 + 8 + 4 * 8 + 2 * 8
+    assert C.sizeof(L.SweepDesc) == C.sizeof(L.PlanDesc) + 8 * 8 + 6 * 8 + 8 + 8 + 4 * 8 + 2 * 8 + 8 + 8 * 8
     assert C.sizeof(L.Triplet) == 8 and L.TRIPLET_DTYPE.itemsize == 8
 
 

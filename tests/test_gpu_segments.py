@@ -211,3 +211,61 @@ def test_registered_shared_memory_receives_results(gpu, golden):
     finally:
         shm.close()
         shm.unlink()
+
+
+@pytest.mark.parametrize("n1", [3, 90])          # whole-run kernel / z-segment scheduler
+def test_peer_gain_maps_receive_the_gathered_result(gpu, golden, n1):
+    """`fpa_sweep_desc.peer_gain`: the sweep kernel also stores each gain into full-size maps (on a multi-GPU box:
+    one per GPU, opened over CUDA IPC -- the fused final gather).  Here two maps on the one device and two
+    sub-range launches: together they must fill both maps with exactly the single-launch result."""
+    import ctypes as C
+    import torch
+    L, lib = gpu._lib, gpu._lib.lib()
+    dev = torch.device("cuda", 0)
+    L.check(lib.fpa_set_device(0))
+    n3 = 1000
+    lam1 = np.linspace(1545e-9, 1555e-9, n1)
+    lam3 = np.linspace(600e-9, 1700e-9, n3)             # includes invalid plans (NaN gains travel too)
+    B = n1 * n3
+    t_l1, t_l3 = torch.from_numpy(lam1).to(dev), torch.from_numpy(lam3).to(dev)
+    t_l2 = torch.tensor([1558e-9], dtype=torch.float64, device=dev)
+    maps = [torch.full((B,), -5.0, dtype=torch.float64, device=dev) for _ in range(2)]
+    ref = torch.empty(B, dtype=torch.float64, device=dev)
+
+    def launch(first, count, gain, peers):
+        t_db = torch.empty(count, dtype=torch.float64, device=dev)
+        t_va = torch.empty(count, dtype=torch.int32, device=dev)
+        t_st = torch.empty(count, dtype=torch.int32, device=dev)
+        nb = int(lib.fpa_yaman4_sweep_scratch_bytes(count))
+        t_scr = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+        d = L.SweepDesc()
+        d.plan.n1, d.plan.n3 = n1, n3
+        d.plan.lambda1, d.plan.lambda2, d.plan.lambda3 = t_l1.data_ptr(), t_l2.data_ptr(), t_l3.data_ptr()
+        gpu.phase_matching.fill_plan_desc(d.plan, _disp(gpu, golden), gpu.phase_matching.PhaseMatchingConfig())
+        d.plan.dbeta, d.plan.valid = t_db.data_ptr(), t_va.data_ptr()
+        A0 = gpu.simulation.make_initial_amplitudes(golden["b4_p_in"])
+        for j in range(4):
+            d.A0[2 * j], d.A0[2 * j + 1] = A0[j].real, A0[j].imag
+        d.p_signal, d.gamma, d.alpha = float(golden["b4_p_in"][2]), 11.5e-3, 1e-4
+        d.z_max, d.dz, d.length_scale, d.save_every = 40.0, 0.2, 1.0, 10
+        d.flags = L.CHECK_NAN
+        d.gain_lin, d.status = gain.data_ptr(), t_st.data_ptr()
+        if count != B:
+            d.first_point, d.n_sub_points = first, count
+        d.n_peers = len(peers)
+        for r, m in enumerate(peers):
+            d.peer_gain[r] = m.data_ptr()
+        L.check(lib.fpa_yaman4_sweep_dev(C.byref(d), t_scr.data_ptr(), nb, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+
+    launch(0, B, ref, [])
+    cut = B // 2 + 17
+    part_a = torch.empty(cut, dtype=torch.float64, device=dev)
+    part_b = torch.empty(B - cut, dtype=torch.float64, device=dev)
+    launch(0, cut, part_a, maps)
+    launch(cut, B - cut, part_b, maps)
+    want = ref.cpu().numpy()
+    assert np.isnan(want).any() and np.isfinite(want).any()
+    for m in maps:
+        assert m.cpu().numpy().tobytes() == want.tobytes()
+    assert torch.cat([part_a, part_b]).cpu().numpy().tobytes() == want.tobytes()
