@@ -23,8 +23,10 @@ metric for every point = 2.5e9 point.RK4-steps.
             B = 1 and 1024, trace write-out), N = 1 only
 
 N > 1 (torchrun, one rank per GPU): the headline is STRONG scaling -- the fixed 1e6-point grid of the
-config is split into N contiguous point ranges, one kernel per GPU, then an NCCL all-gather of the gain
-map; the weak-scaling figure (1e6 points per GPU) is reported alongside under "weak".
+config is split into N contiguous point ranges, one kernel per GPU; the final gather of the gain map is
+done by the sweep kernel itself (NVLink peer stores into the full-size map of every GPU, opened over CUDA
+IPC; `--gather nccl` or a box without peer access: an NCCL all-gather after the kernel); the weak-scaling
+figure (1e6 points per GPU, NCCL all-gather) is reported alongside under "weak".
 `--impl reference` times the CPU arm with all host cores; only rank 0 works.
 """
 from __future__ import annotations
@@ -630,8 +632,9 @@ def run_ours(args) -> None:
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": e2e_api, "variants": e2e_variants},
         "gpu_launches": args.steps,              # one sweep kernel per step on every rank
-        "step_breakdown": {**parts, "note": "rank 0, CUDA events between the pieces of a step; the rest of a step is launch gaps "
-                                            "and, at N > 1, waiting for the slowest rank inside the all-gather"},
+        "step_breakdown": {**parts, "note": "rank 0, CUDA events between the pieces of a step; gather_ms is the NCCL all-gather incl. "
+                                            "waiting for the slowest rank (~0 when the sweep kernel gathers by peer stores); the "
+                                            "rest of a step is launch gaps"},
         "clocks": clocks,
         "roofline": {"bound": "fp64_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "frac_of_nominal": achieved_tf / nominal_tf,

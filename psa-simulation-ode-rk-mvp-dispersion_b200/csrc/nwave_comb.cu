@@ -479,6 +479,16 @@ __device__ __forceinline__ void roll8_mac(const double2* __restrict__ a, const d
     for (int i = i0; i < i1; i += 8) {
         wp += 9;  // the next 8 words of w (one spare word in between)
         // operands of the next term are requested before this term's 32 FMAs
+#ifdef FPA_EXP_NOLOADS   /* timing experiment only (results are wrong): the FMA stream without its shared-memory loads */
+#define FPA_TERM(K)                                                                     \
+        {                                                                               \
+            const double2 nw = make_double2(win[K].y, win[K].x);                        \
+            const double2 an = make_double2(av.y, av.x);                                \
+            term8<K>(re, im, av, win);                                                  \
+            win[K] = nw;                                                                \
+            av = an;                                                                    \
+        }
+#else
 #define FPA_TERM(K)                                                                     \
         {                                                                               \
             const double2 nw = wp[K];                                                   \
@@ -487,6 +497,7 @@ __device__ __forceinline__ void roll8_mac(const double2* __restrict__ a, const d
             win[K] = nw;                                                                \
             av = an;                                                                    \
         }
+#endif
         FPA_TERM(0) FPA_TERM(1) FPA_TERM(2) FPA_TERM(3) FPA_TERM(4) FPA_TERM(5) FPA_TERM(6) FPA_TERM(7)
 #undef FPA_TERM
         ap += 9;

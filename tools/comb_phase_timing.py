@@ -12,7 +12,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import __graft_entry__ as entry
 out = entry.BUILD / "libfpa_b200_timing.so"
-flags = list(entry.NVCC_FLAGS) + ["-DFPA_COMB_TIMING", "-DFPA_SASS_PASS=0"]
+flags = list(entry.NVCC_FLAGS) + ["-DFPA_COMB_TIMING", "-DFPA_SASS_PASS=0"] + [f for f in os.environ.get("FPA_TIMING_FLAGS", "").split() if f]
 res = subprocess.run([entry._nvcc(), *flags, "-o", str(out), *[str(entry.CSRC / s) for s in entry.SOURCES]], capture_output=True, text=True)
 if res.returncode: raise SystemExit(res.stderr)
 fpa = entry.load_package()
