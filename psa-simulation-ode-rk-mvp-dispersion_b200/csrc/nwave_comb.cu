@@ -1014,8 +1014,8 @@ int nwave_comb_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     // fit into a CTA's shared memory); below that one CTA per point, for latency
     const size_t smem_w1 = comb_point_doubles(N, M, kSk8) * sizeof(double);
     const bool   wide = d->n_points >= 4 * (int64_t)sms && smem_w1 <= 200 * 1024;
-    static const int old_wide = getenv("FPA_COMB_TILE4") ? atoi(getenv("FPA_COMB_TILE4")) : 0;  // tools: round-1 mapping
-    static const int force_l = getenv("FPA_COMB_LANES") ? atoi(getenv("FPA_COMB_LANES")) : 0;  // tools: 32 | 16
+    const int old_wide = getenv("FPA_COMB_TILE4") ? atoi(getenv("FPA_COMB_TILE4")) : 0;  // tools: round-1 mapping
+    const int force_l = getenv("FPA_COMB_LANES") ? atoi(getenv("FPA_COMB_LANES")) : 0;  // tools: 32 | 16
     // lanes per point: half a warp once the batch still gives every sub-partition two warps that way.  (Two
     // warps per point -- the W = 2 instantiation of the kernel, tiles split over the warps, named barriers -- was
     // measured for the small batches and lost: B = 1024 5.8e7 against 6.6e7 point.steps/s, B = 592 5.8e7 against 6.3e7.)

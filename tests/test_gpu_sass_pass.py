@@ -108,3 +108,24 @@ def test_segment_scheduler_kernels_bit_identical(gpu, golden):
                 cfg3, gamma=10.0, alpha=alpha, delta_beta=db, p_in=[0.1, 0.1, 1e-5, 0.0], length_unit="km", outputs=outputs)
             a, b = _both(gpu, run)
             _same(a, b)
+
+
+@pytest.mark.parametrize("batch, lanes", [(640, "32"), (640, "16")])
+def test_comb_batch_kernel_bit_identical(gpu, batch, lanes, monkeypatch):
+    """`nwave_comb8_kernel` goes through the pass in flags-only mode (ptxas' order kept, yield hints cleared,
+    operand-reuse flags set): both lane mappings must agree bit for bit with the ptxas-schedule build."""
+    monkeypatch.setenv("FPA_COMB_LANES", lanes)     # read once per library instance, i.e. once per build here
+    nw = gpu.nwave
+    w0 = 2 * np.pi * 299792458.0 / 1550e-9
+    for lines in (range(-32, 32), range(-10, 11), [0, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89]):
+        plan = nw.uniform_comb_plan(w0, 2 * np.pi * 100e9, lines)
+        N = plan.n_waves
+        beta = nw.beta_per_wave(plan, gpu.dispersion.DispersionParams(omega_ref=w0, beta2=-2.57e-29, beta3=3.30e-41,
+                                                                       beta4=-1.63e-55))
+        rng = np.random.default_rng(N)
+        A0 = np.sqrt(rng.uniform(1e-6, 0.2, (batch, N))) * np.exp(1j * rng.uniform(0, 6.28, (batch, N)))
+        cfg = gpu.config.custom_simulation_config(z_max=15.0, dz=0.1, save_every=50)
+        run = lambda: nw.run_nwave_simulation(cfg, plan, gamma=11.5e-3, alpha=2e-4, A0=A0, beta=beta,   # noqa: E731
+                                              outputs=("trace", "end", "pmax"), form="comb")
+        a, b = _both(gpu, run)
+        _same(a, b)
