@@ -1016,12 +1016,13 @@ int nwave_comb_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     const bool   wide = d->n_points >= 4 * (int64_t)sms && smem_w1 <= 200 * 1024;
     const int old_wide = getenv("FPA_COMB_TILE4") ? atoi(getenv("FPA_COMB_TILE4")) : 0;  // tools: round-1 mapping
     const int force_l = getenv("FPA_COMB_LANES") ? atoi(getenv("FPA_COMB_LANES")) : 0;  // tools: 32 | 16
-    // lanes per point: half a warp once the batch still gives every sub-partition two warps that way.  (Two
-    // warps per point -- the W = 2 instantiation of the kernel, tiles split over the warps, named barriers -- was
-    // measured for the small batches and lost: B = 1024 5.8e7 against 6.6e7 point.steps/s, B = 592 5.8e7 against 6.3e7.)
-    const int lanes = force_l ? force_l : d->n_points >= 16 * (int64_t)sms * 4 ? 16 : 32;
-    // CTA per point: 4 warps, tiles of 2, sums split 4 ways -- the fastest of the seven (W, TILE, SPLIT)
-    // shapes tried for single runs (5.8 us per step at N = 64, 4.3 at N = 21; the others 5.9 .. 7.3)
+    // lanes per point: one warp.  Half a warp per point (two points per warp in lock-step: half the loads and
+    // shuffles per FMA, but 200 registers and one CTA per SM) was ahead for B >= 9 472 until the correlation
+    // bodies got their operand-reuse flags from the SASS pass (9.2e7 against 8.9e7); since then one warp per point
+    // is at least as fast at every batch size (B = 9 472: 9.3e7 / 9.2e7) and the half-warp instantiation is kept
+    // for FPA_COMB_LANES=16 only.  (Two warps per point -- the W = 2 instantiation of the kernel, tiles split over
+    // the warps, named barriers -- was measured for the small batches and lost: B = 1024 5.8e7 against 6.6e7.)
+    const int lanes = force_l ? force_l : 32;
     cudaError_t e = !wide ? comb_launch_w<4, 2, 4>(p, sms, st)
                     : old_wide ? comb_launch_w<1, 4, 2>(p, sms, st)
                     : lanes == 16 ? comb8_launch<16, 1>(p, sms, st) : comb8_launch<32, 1>(p, sms, st);
