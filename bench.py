@@ -250,27 +250,47 @@ class ClockSampler:
 class PeerMaps:
     """One full-size gain map per GPU of the box, each opened in every rank (CUDA IPC through the C ABI): the
     sweep kernel stores each point's gain into all of them (`fpa_sweep_desc.peer_gain`), which IS the final
-    gather -- no collective after the kernel."""
+    gather -- no collective after the kernel.  `setup` returns None (on every rank alike) when any rank cannot
+    allocate, export or open a map; every rank takes part in every collective of the set-up whatever happened
+    locally, so a failure on one rank cannot leave the others waiting."""
 
-    def __init__(self, fpa, dist, torch, world, rank, local, n_points):
+    @classmethod
+    def setup(cls, fpa, dist, torch, world, rank, local, n_points):
+        self = cls()
         L, lib = fpa._lib, fpa._lib.lib()
-        self.L, self.lib, self.rank, self.n = L, lib, rank, n_points
-        self.own = C.c_void_p()
-        L.check(lib.fpa_dev_alloc(C.byref(self.own), n_points * 8, local))
-        handle = (C.c_char * 64)()
-        L.check(lib.fpa_ipc_export(self.own, handle))
+        self.lib, self.n, self.torch, self.dev = lib, n_points, torch, torch.device("cuda", local)
+        self.own, self.ptrs, self.opened = C.c_void_p(), [], []
+        handle, why = None, ""
+        try:
+            L.check(lib.fpa_dev_alloc(C.byref(self.own), n_points * 8, local))
+            buf = (C.c_char * 64)()
+            L.check(lib.fpa_ipc_export(self.own, buf))
+            handle = bytes(buf.raw)
+        except Exception as exc:                      # noqa: BLE001
+            why = repr(exc)
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle.raw))
-        self.ptrs, self.opened = [], []
-        for r in range(world):
-            if r == rank:
-                self.ptrs.append(self.own.value)
-                continue
-            q = C.c_void_p()
-            L.check(lib.fpa_ipc_open(handles[r], C.byref(q)))
-            self.ptrs.append(q.value)
-            self.opened.append(q)
-        self.torch, self.dev = torch, torch.device("cuda", local)
+        dist.all_gather_object(handles, handle)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                for r in range(world):
+                    if r == rank:
+                        self.ptrs.append(self.own.value)
+                        continue
+                    q = C.c_void_p()
+                    L.check(lib.fpa_ipc_open(handles[r], C.byref(q)))
+                    self.ptrs.append(q.value)
+                    self.opened.append(q)
+            except Exception as exc:                  # noqa: BLE001
+                ok, why = False, repr(exc)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            return self
+        if why:
+            print(f"rank {rank}: peer maps unavailable ({why}); falling back to the NCCL all-gather", file=sys.stderr)
+        self.close(dist)
+        return None
 
     def own_map(self):
         """This rank's map as a torch tensor (no copy)."""
@@ -283,8 +303,11 @@ class PeerMaps:
     def close(self, dist):
         for q in self.opened:
             self.lib.fpa_ipc_close(q)
+        self.opened = []
         dist.barrier()              # nobody still has this rank's map open
-        self.lib.fpa_dev_free(self.own)
+        if self.own.value:
+            self.lib.fpa_dev_free(self.own)
+            self.own = C.c_void_p()
 
 
 class DeviceSweep:
@@ -432,16 +455,8 @@ def run_ours(args) -> None:
     # the final gather: peer stores by the sweep kernel itself (default), or an NCCL all-gather after it
     peers, gather_how = None, "none (one GPU)"
     if world > 1:
-        ok = torch.zeros(1, dtype=torch.int32, device=dev)
         if args.gather == "peer":
-            try:
-                peers = PeerMaps(fpa, dist, torch, world, rank, local, total_points)
-                ok += 1
-            except Exception as exc:          # noqa: BLE001 -- no peer access / IPC on this box: NCCL instead
-                print(f"rank {rank}: peer maps unavailable ({exc!r}); falling back to the NCCL all-gather", file=sys.stderr)
-        dist.all_reduce(ok)                   # all ranks or none
-        if peers is not None and int(ok.item()) != world:
-            peers = None
+            peers = PeerMaps.setup(fpa, dist, torch, world, rank, local, total_points)
         gather_how = ("kernel: NVLink peer stores into the full-size map of every GPU (fpa_sweep_desc.peer_gain)"
                       if peers is not None else "NCCL all_gather_into_tensor after the kernel")
     sweep = DeviceSweep(fpa, torch, dev, N1, lo, hi - lo, disp, pm_cfg, peer_maps=peers.ptrs if peers else None)
