@@ -244,14 +244,33 @@ def enumerate_triplets_omega(omega, atol: float = 0.0, rtol: float = 1e-12) -> t
     return table, rows
 
 
+def factor_table(n_waves: int, table, row_ptr) -> tuple[np.ndarray, int]:
+    """(blob, n_classes) of `fpa_nwave_factor_table`: the factored form of a triplet table the table kernel
+    integrates from (pair products once per RHS, one cell per (n, m)); `fpa_nwave_rk4_batch_host` builds it
+    itself, callers of the `_dev` entry upload the blob and point `fpa_nwave_desc.factored` at it."""
+    table = np.ascontiguousarray(table, dtype=_lib.TRIPLET_DTYPE)
+    rows = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    L = _lib.lib()
+    nc = C.c_int32()
+    nb = L.fpa_nwave_factor_table(int(n_waves), ptr(table) if table.size else None, ptr(rows), table.size, None, 0, C.byref(nc))
+    if nb < 0:
+        raise ValueError(_lib.last_error())
+    blob = np.zeros(nb, dtype=np.uint8)
+    if L.fpa_nwave_factor_table(int(n_waves), ptr(table) if table.size else None, ptr(rows), table.size, ptr(blob), nb, C.byref(nc)) != nb:
+        raise ValueError(_lib.last_error())
+    return blob, int(nc.value)
+
+
 def nwave_batch(beta, gamma, alpha, A0, table, row_ptr, *, z0=0.0, z_max, n_steps, save_every=1,
                 trace=False, end=True, pmax=False, check_nan=True, n_points: Optional[int] = None,
-                grid_index=None, force_table: bool = False, force_comb: bool = False,
+                grid_index=None, force_table: bool = False, force_comb: bool = False, plain_table: bool = False,
                 device: Optional[int] = None, devices=None) -> dict:
     """B points of the N-wave model through `fpa_nwave_rk4_batch_host` (`devices=[...]`:
     `fpa_nwave_rk4_batch_multi_host`).  With `grid_index` (integer grid position of every wave) the
     library may integrate the convolution form of the same ODE (O(span^2) per RHS): it does so for plans
-    within that kernel's limits unless they are sparse; `force_table` / `force_comb` override the choice."""
+    within that kernel's limits unless they are sparse; `force_table` / `force_comb` override the choice.
+    The table kernel integrates from the factored table (`factor_table`); `plain_table` makes it walk the entry
+    list instead (the round-1 kernel, kept as the independent check)."""
     A0 = c128(A0)
     N = A0.shape[-1]
     beta = f64(beta)
@@ -281,7 +300,7 @@ def nwave_batch(beta, gamma, alpha, A0, table, row_ptr, *, z0=0.0, z_max, n_step
     d.triplets, d.row_ptr, d.n_triplets = (ptr(table) if table.size else None), ptr(rows), table.size
     d.z0, d.z_max, d.n_steps, d.save_every = float(z0), float(z_max), n_steps, save_every
     d.flags = (_flags(trace, end, pmax, check_nan, False) | (_lib.NWAVE_TABLE if force_table else 0) |
-               (_lib.NWAVE_COMB if force_comb else 0))
+               (_lib.NWAVE_COMB if force_comb else 0) | (_lib.NWAVE_PLAIN if plain_table else 0))
     d.A_trace, d.A_end, d.Pmax = ptr(out.get("A_trace")), ptr(out.get("A_end")), ptr(out.get("Pmax"))
     d.status = ptr(out["status"])
     slots = None

@@ -19,6 +19,7 @@ LIB_PATH = PKG_DIR / "libfpa_b200.so"
 # status codes / flags (include/fpa_b200.h)
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 OUT_TRACE, OUT_END, OUT_PMAX, CHECK_NAN, PHASE_EXACT, UNIFORM_PHYSICS, NWAVE_TABLE, NWAVE_COMB = 1, 2, 4, 8, 16, 32, 64, 128
+NWAVE_PLAIN = 256
 POINT_OK = -1
 PM_GENERAL_TAYLOR, PM_SYMMETRIC_EVEN, PM_PROVIDED = 0, 1, 2
 MAX_TAYLOR_ORDER = 12
@@ -96,7 +97,8 @@ class NwaveDesc(C.Structure):
         ("flags", C.c_uint32), ("reserved1", C.c_uint32),
         ("A_trace", C.c_void_p), ("A_end", C.c_void_p), ("Pmax", C.c_void_p),
         ("status", C.c_void_p),
-        ("grid_slot", C.c_void_p), ("grid_span", C.c_int32), ("reserved2", C.c_int32),
+        ("grid_slot", C.c_void_p), ("grid_span", C.c_int32), ("n_classes", C.c_int32),
+        ("factored", C.c_void_p),
     ]
 
 
@@ -124,6 +126,7 @@ SIGNATURES = {
                                             C.c_double, C.c_int64, C.c_int64, C.c_void_p, C.c_uint32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fpa_enumerate_triplets": (C.c_int64, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fpa_nwave_factor_table": (C.c_int64, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "fpa_enumerate_triplets_omega": (C.c_int64, [C.c_int32, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64,
                                                  C.c_void_p]),
     "fpa_nwave_rk4_batch_multi_host": (C.c_int, [C.POINTER(NwaveDesc), C.c_int, C.POINTER(C.c_int)]),

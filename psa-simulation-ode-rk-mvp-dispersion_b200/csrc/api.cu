@@ -794,9 +794,18 @@ static int nwave_host_launch(const fpa_nwave_desc* d, int device, PendingNwave* 
     const size_t n_a = d->alpha_stride ? B : 1, n_A0 = (d->A0_stride ? B : 1) * N * 2;
     const size_t n_t = comb ? 0 : (size_t)d->n_triplets;
     const size_t n_tr = trace ? B * ns * N * 2 : 0;
+    // the table kernel gets the factored form of the table (unless the caller insists on the entry list)
+    std::vector<unsigned char> blob;
+    int32_t                    n_classes = 0;
+    if (!comb && !(d->flags & FPA_NWAVE_PLAIN) && N <= 128) {
+        const int64_t nb = fpa_nwave_factor_table((int32_t)N, d->triplets, d->row_ptr, d->n_triplets, nullptr, 0, &n_classes);
+        if (nb < 0) return FPA_ERR_INVALID;
+        blob.resize((size_t)nb);
+        if (fpa_nwave_factor_table((int32_t)N, d->triplets, d->row_ptr, d->n_triplets, blob.data(), nb, &n_classes) != nb) return FPA_ERR_INVALID;
+    }
     void* ws = nullptr;
     FPA_TRY(workspace(device, 5,
-                      Carver::need(n_b * 8) + Carver::need(n_g * 8) + Carver::need(n_a * 8) +
+                      Carver::need(blob.size()) + Carver::need(n_b * 8) + Carver::need(n_g * 8) + Carver::need(n_a * 8) +
                           Carver::need(n_A0 * 8) + Carver::need(n_t * sizeof(fpa_triplet)) +
                           Carver::need((N + 1) * 8) + Carver::need(n_tr * 8) +
                           Carver::need(B * N * 16) + Carver::need(B * N * 8) + Carver::need(B * 4) +
@@ -817,7 +826,9 @@ static int nwave_host_launch(const fpa_nwave_desc* d, int device, PendingNwave* 
     double*      Pm   = cv.take<double>(B * N);
     int32_t*     stt  = cv.take<int32_t>(B);
     int32_t*     slot = cv.take<int32_t>(N);
+    unsigned char* fact = cv.take<unsigned char>(blob.size());
     if (comb) FPA_TRY(up(slot, d->grid_slot, N * 4, st));
+    if (!blob.empty()) FPA_TRY(up(fact, blob.data(), blob.size(), st));
     FPA_TRY(up(beta, d->beta, n_b * 8, st));
     FPA_TRY(up(gam, d->gamma, n_g * 8, st));
     FPA_TRY(up(alp, d->alpha, n_a * 8, st));
@@ -838,6 +849,8 @@ static int nwave_host_launch(const fpa_nwave_desc* d, int device, PendingNwave* 
     dd.Pmax     = pmax ? Pm : nullptr;
     dd.status   = stt;
     dd.grid_slot = comb ? slot : nullptr;
+    dd.factored  = blob.empty() ? nullptr : fact;
+    dd.n_classes = n_classes;
     dd.flags = (d->flags & ~(FPA_NWAVE_TABLE | FPA_NWAVE_COMB)) | (comb ? FPA_NWAVE_COMB : FPA_NWAVE_TABLE);  // decided above
     FPA_TRY(nwave_dispatch(&dd, st));
     pn->st   = st;

@@ -17,6 +17,11 @@
 #include "fpa_common.cuh"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
 #include <vector>
 
 namespace fpa {
@@ -43,7 +48,36 @@ struct NwaveParams {
     double*            Pmax;
     int32_t*           status;
     int                check;
+    const unsigned char* fact;        // factored table (FactHeader + arrays, see below) or NULL
+    int                n_classes;
 };
+
+// Factored form of a triplet table (host: fpa_nwave_factor_table below).  The entries of row n are grouped by
+// their conjugated wave m; the (k, l, weight) list of a group is a CLASS, and groups with the same list share it:
+//   R_n = sum_m conj(At_m) * T_{c(n,m)} - At_n * sum_m w_own(n,m) P_m,     T_c = sum_{(k,l,w) in c} w At_k At_l.
+// For a table that came from a frequency plan every group of the same sum frequency w_n + w_m holds the same
+// pairs except its own {n, m} (the enumerator's "m not in {k, l}"), so the factoriser may add that pair to the
+// group (weight 1 for n == m, else 2) and take it out again through w_own -- then N = 64 has 127 classes with
+// 2 080 pairs in all and 4 096 (n, m) cells instead of 84 320 entries.  Any table factors (worst case one class
+// per cell); nothing about the plan is assumed.  Modes: 0 no own pairs (w_own = 0); 1 own pairs where a group
+// has entries, w_own matrix; 2 own pairs in EVERY cell, so sum_m w_own P_m = 2 S - P_n needs no matrix.
+//
+// Layout for the kernel: pair records {k*16, l*16, weight} with every class padded to a multiple of 4 (weight 0);
+// the cell map in LANE ORDER -- row n is shared by lpr = 2^lpr_log lanes, lane r takes m = r, r + lpr, ... and
+// its cells are contiguous, four byte offsets into T per 16-byte load (empty cells point at a zero slot T[C]).
+struct FactHeader {
+    uint32_t magic;
+    int32_t  n_waves, n_classes, n_pairs, mode, lpr_log, cpl4;
+    int32_t  off_cls, off_pairs, off_cmap, off_wown;   // bytes from the start of the blob
+    int32_t  bytes;
+};
+struct FactPair {
+    uint16_t k16, l16;   // byte offsets of At_k, At_l (index * 16)
+    float    w;
+};
+constexpr uint32_t kFactMagic   = 0x32504146u;   // "FAP2"
+constexpr int      kFactMaxCls  = 1 << 20;
+constexpr int      kFactThreads = 256;           // lanes per row = kFactThreads / N (a power of two, 1..32)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -56,6 +90,7 @@ struct Smem {
     double *y, *ys, *yn, *At, *E, *beta, *P, *red;
     int*                rows;
     const fpa_triplet*  table;
+    double2*            T;      // factored form: class sums, in place of rows | table
 };
 
 __device__ __forceinline__ Smem carve(double* base, int N, const NwaveParams& p) {
@@ -69,6 +104,7 @@ __device__ __forceinline__ Smem carve(double* base, int N, const NwaveParams& p)
     s.P    = s.beta + N;
     s.red  = s.P + N;
     s.rows = reinterpret_cast<int*>(s.red + 34);
+    s.T    = reinterpret_cast<double2*>(s.red + 34);
     // table is 8-byte aligned: (N+1) ints rounded up to an even count
     s.table = reinterpret_cast<const fpa_triplet*>(s.rows + ((N + 2) & ~1));
     return s;
@@ -161,6 +197,189 @@ __device__ double rhs_stage(const Smem& s, const NwaveParams& p, const fpa_tripl
     return S;
 }
 
+#ifdef FPA_FACT_TIMING   // tools/fact_phase_timing.py: thread 0 of point 0 accumulates clock64() between the phases
+__device__ long long g_fact_ticks[8];
+#define FPA_FTICK(k)                                        \
+    do {                                                    \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {          \
+            const long long t_now = clock64();              \
+            g_fact_ticks[k] += t_now - t_last;              \
+            t_last = t_now;                                 \
+        }                                                   \
+    } while (0)
+#else
+#define FPA_FTICK(k)
+#endif
+
+struct FactView {
+    const int32_t*  cls;
+    const FactPair* pairs;
+    const uint32_t* cmap;
+    const int16_t*  wown;
+    int             C, mode, lpr_log, cpl4, ok;
+};
+
+__device__ __forceinline__ FactView fact_view(const NwaveParams& p) {
+    const FactHeader* h = reinterpret_cast<const FactHeader*>(p.fact);
+    FactView          f;
+    f.ok      = h->magic == kFactMagic && h->n_waves == p.n_waves && h->n_classes == p.n_classes;
+    f.cls     = reinterpret_cast<const int32_t*>(p.fact + h->off_cls);
+    f.pairs   = reinterpret_cast<const FactPair*>(p.fact + h->off_pairs);
+    f.cmap    = reinterpret_cast<const uint32_t*>(p.fact + h->off_cmap);
+    f.wown    = reinterpret_cast<const int16_t*>(p.fact + h->off_wown);
+    f.C       = h->n_classes;
+    f.mode    = h->mode;
+    f.lpr_log = h->lpr_log;
+    f.cpl4    = h->cpl4;
+    return f;
+}
+
+// The same stage as rhs_stage through the factored table: class sums with 4 lanes per class, then the rows with
+// lpr lanes per row.  Phases are the exact sincos of rhs_stage.
+__device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView& f, double z, double gamma,
+                             double nha, double wa, double wb, bool last) {
+    const int N = p.n_waves;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const double2*       At2 = reinterpret_cast<const double2*>(s.At);
+    const unsigned char* Atb = reinterpret_cast<const unsigned char*>(s.At);
+    const unsigned char* Tb  = reinterpret_cast<const unsigned char*>(s.T);
+#ifdef FPA_FACT_TIMING
+    long long t_last = clock64();
+#endif
+
+    double part = 0.0;
+    for (int j = tid; j < N; j += blockDim.x) {
+        double sn, cs;
+        sincos(s.beta[j] * z, &sn, &cs);
+        const double xr = s.ys[2 * j], xi = s.ys[2 * j + 1];
+        s.E[2 * j]      = cs;
+        s.E[2 * j + 1]  = sn;
+        s.At[2 * j]     = fma(-xi, sn, xr * cs);
+        s.At[2 * j + 1] = fma(xr, sn, xi * cs);
+        const double P  = fma(xi, xi, xr * xr);
+        s.P[j] = P;
+        part += P;
+    }
+    FPA_FTICK(0);
+    part = warp_sum(part);
+    if (lane == 0) s.red[warp] = part;
+    __syncthreads();
+    FPA_FTICK(1);
+    double S = 0.0, S1 = 0.0;
+    for (int w = 0; w + 1 < nwarps; w += 2) {
+        S += s.red[w];
+        S1 += s.red[w + 1];
+    }
+    if (nwarps & 1) S += s.red[nwarps - 1];
+    S += S1;
+
+    // class sums T_c: four lanes per class, every class a multiple of four pairs; two pairs of a lane in flight
+    const int sub4 = tid & 3;
+    auto      pair_term = [&](const uint2 u, double& qr, double& qi) {
+        const double2 a = *reinterpret_cast<const double2*>(Atb + (u.x & 0xFFFFu));
+        const double2 b = *reinterpret_cast<const double2*>(Atb + (u.x >> 16));
+        const double  w = (double)__uint_as_float(u.y);
+        const double  pr = fma(-a.y, b.y, a.x * b.x);
+        const double  pi = fma(a.x, b.y, a.y * b.x);
+        qr = fma(w, pr, qr);
+        qi = fma(w, pi, qi);
+    };
+    for (int base = 0; base < f.C; base += (int)(blockDim.x >> 2)) {
+        const int c = base + (tid >> 2);
+        double    qr = 0.0, qi = 0.0, q2 = 0.0, j2 = 0.0;
+        if (c < f.C) {
+            const uint2* pp = reinterpret_cast<const uint2*>(f.pairs);
+            const int    e1 = __ldg(f.cls + c + 1);
+            int          e = __ldg(f.cls + c) + sub4;
+            for (; e + 4 < e1; e += 8) {
+                const uint2 u0 = __ldg(pp + e), u1 = __ldg(pp + e + 4);
+                pair_term(u0, qr, qi);
+                pair_term(u1, q2, j2);
+            }
+            if (e < e1) pair_term(__ldg(pp + e), qr, qi);
+            qr += q2;
+            qi += j2;
+        }
+        qr += __shfl_xor_sync(0xffffffffu, qr, 1);
+        qi += __shfl_xor_sync(0xffffffffu, qi, 1);
+        qr += __shfl_xor_sync(0xffffffffu, qr, 2);
+        qi += __shfl_xor_sync(0xffffffffu, qi, 2);
+        if (c < f.C && sub4 == 0) s.T[c] = make_double2(qr, qi);
+    }
+    FPA_FTICK(2);
+    __syncthreads();
+    FPA_FTICK(3);
+
+    // rows: lpr lanes per row, four cells per 16-byte load of the lane-ordered map; cells beyond N point at the
+    // zero slot (their At index is clamped), so the body has no branches and its eight loads go out together
+    const int lpr_log = f.lpr_log, lpr = 1 << lpr_log, rsub = tid & (lpr - 1);
+    for (int base = 0; base < N; base += (int)(blockDim.x >> lpr_log)) {
+        const int n = base + (tid >> lpr_log);
+        double    rr = 0.0, ri = 0.0, r2 = 0.0, i2 = 0.0, r3 = 0.0, i3 = 0.0, r4 = 0.0, i4 = 0.0, cw = 0.0;
+        if (n < N) {
+            const uint4* cm = reinterpret_cast<const uint4*>(f.cmap + ((size_t)n * lpr + rsub) * f.cpl4);
+            uint4        o = __ldg(cm);
+            for (int i = 0, m = rsub; i < f.cpl4; i += 4, m += 4 * lpr) {
+                const uint4   on = __ldg(cm + (i + 4 < f.cpl4 ? (i >> 2) + 1 : 0));
+                const double2 t0 = *reinterpret_cast<const double2*>(Tb + o.x);
+                const double2 t1 = *reinterpret_cast<const double2*>(Tb + o.y);
+                const double2 t2 = *reinterpret_cast<const double2*>(Tb + o.z);
+                const double2 t3 = *reinterpret_cast<const double2*>(Tb + o.w);
+                const double2 b0 = At2[min(m, N - 1)], b1 = At2[min(m + lpr, N - 1)];
+                const double2 b2 = At2[min(m + 2 * lpr, N - 1)], b3 = At2[min(m + 3 * lpr, N - 1)];
+                rr = fma(t0.x, b0.x, fma(t0.y, b0.y, rr));   // T * conj(At_m)
+                ri = fma(t0.y, b0.x, fma(-t0.x, b0.y, ri));
+                r2 = fma(t1.x, b1.x, fma(t1.y, b1.y, r2));
+                i2 = fma(t1.y, b1.x, fma(-t1.x, b1.y, i2));
+                r3 = fma(t2.x, b2.x, fma(t2.y, b2.y, r3));
+                i3 = fma(t2.y, b2.x, fma(-t2.x, b2.y, i3));
+                r4 = fma(t3.x, b3.x, fma(t3.y, b3.y, r4));
+                i4 = fma(t3.y, b3.x, fma(-t3.x, b3.y, i4));
+                o = on;
+            }
+            rr = (rr + r2) + (r3 + r4);
+            ri = (ri + i2) + (i3 + i4);
+            if (f.mode == 1) {
+                const int16_t* wo = f.wown + n * N;
+                for (int m = rsub; m < N; m += lpr) cw = fma((double)__ldg(wo + m), s.P[m], cw);
+            }
+        }
+        for (int o = lpr >> 1; o > 0; o >>= 1) {
+            rr += __shfl_xor_sync(0xffffffffu, rr, o);
+            ri += __shfl_xor_sync(0xffffffffu, ri, o);
+            if (f.mode == 1) cw += __shfl_xor_sync(0xffffffffu, cw, o);
+        }
+        if (n < N && rsub == 0) {
+            const double xr = s.ys[2 * n], xi = s.ys[2 * n + 1];
+            const double er = s.E[2 * n], ei = s.E[2 * n + 1];
+            // the own pairs the factoriser added come out again: R -= At_n * sum_m w_own P_m
+            if (f.mode == 2) cw = (S + S) - s.P[n];
+            rr = fma(-cw, s.At[2 * n], rr);
+            ri = fma(-cw, s.At[2 * n + 1], ri);
+            const double fr = fma(ri, ei, rr * er);
+            const double fi = fma(ri, er, -(rr * ei));
+            const double G  = gamma * ((S + S) - s.P[n]);
+            const double kr = fma(nha, xr, -fma(G, xi, gamma * fi));
+            const double ki = fma(nha, xi, fma(G, xr, gamma * fr));
+            if (last) {
+                s.y[2 * n]     = fma(wa, kr, s.yn[2 * n]);
+                s.y[2 * n + 1] = fma(wa, ki, s.yn[2 * n + 1]);
+            } else {
+                const double a = s.y[2 * n], bq = s.y[2 * n + 1];
+                s.yn[2 * n]     = fma(wa, kr, s.yn[2 * n]);
+                s.yn[2 * n + 1] = fma(wa, ki, s.yn[2 * n + 1]);
+                s.ys[2 * n]     = fma(wb, kr, a);
+                s.ys[2 * n + 1] = fma(wb, ki, bq);
+            }
+        }
+    }
+    FPA_FTICK(4);
+    __syncthreads();
+    FPA_FTICK(5);
+    return S;
+}
+
+template <bool FACT>
 __global__ void nwave_rk4_kernel(const NwaveParams p) {
     extern __shared__ double smem_raw[];
     const int     N = p.n_waves;
@@ -178,14 +397,32 @@ __global__ void nwave_rk4_kernel(const NwaveParams p) {
         s.y[2 * j] = re;
         s.y[2 * j + 1] = im;
     }
-    for (int j = tid; j <= N; j += blockDim.x) s.rows[j] = (int)p.row_ptr[j];
     const fpa_triplet* table = p.triplets;
-    if (p.table_in_smem) {
-        fpa_triplet* dst = const_cast<fpa_triplet*>(s.table);
-        for (int64_t e = tid; e < p.n_triplets; e += blockDim.x) dst[e] = p.triplets[e];
-        table = s.table;
+    FactView           fv = {};
+    if (FACT) {
+        fv = fact_view(p);
+        if (fv.ok && tid == 0) s.T[fv.C] = make_double2(0.0, 0.0);   // the slot empty cells point at
+    } else {
+        for (int j = tid; j <= N; j += blockDim.x) s.rows[j] = (int)p.row_ptr[j];
+        if (p.table_in_smem) {
+            fpa_triplet* dst = const_cast<fpa_triplet*>(s.table);
+            for (int64_t e = tid; e < p.n_triplets; e += blockDim.x) dst[e] = p.triplets[e];
+            table = s.table;
+        }
     }
     __syncthreads();
+    if (FACT && !fv.ok) {   // not the blob of this plan: no result rather than a wrong one
+        if (p.status && tid == 0) p.status[b] = 0;
+        if (p.A_end)
+            for (int j = tid; j < 2 * N; j += blockDim.x) p.A_end[b * 2 * N + j] = qnan();
+        if (p.Pmax)
+            for (int j = tid; j < N; j += blockDim.x) p.Pmax[b * N + j] = qnan();
+        return;
+    }
+    auto stage = [&](double z, double wa, double wb, bool last) {
+        return FACT ? fact_stage(s, p, fv, z, gamma, nha, wa, wb, last)
+                    : rhs_stage(s, p, table, z, gamma, nha, wa, wb, last);
+    };
 
     double* tr = p.A_trace ? p.A_trace + b * p.n_saved * 2 * N : nullptr;
     if (tr) {
@@ -226,15 +463,15 @@ __global__ void nwave_rk4_kernel(const NwaveParams p) {
         }
         __syncthreads();
 
-        const double S = rhs_stage(s, p, table, zi, gamma, nha, h6, hh, false);
+        const double S = stage(zi, h6, hh, false);
         if (p.check && i > 0 && bad == FPA_POINT_OK && nonfinite(S)) {
             int nf = 0;
             for (int j = tid; j < 2 * N; j += blockDim.x) nf |= nonfinite(s.y[j]) ? 1 : 0;
             if (__syncthreads_or(nf)) bad = i - 1;
         }
-        rhs_stage(s, p, table, zi + hh, gamma, nha, h3, hh, false);
-        rhs_stage(s, p, table, zi + hh, gamma, nha, h3, h, false);
-        rhs_stage(s, p, table, zi + h, gamma, nha, h6, 0.0, true);
+        stage(zi + hh, h3, hh, false);
+        stage(zi + hh, h3, h, false);
+        stage(zi + h, h6, 0.0, true);
         zi = zn;
 
         if (--save_ctr == 0) {
@@ -259,6 +496,15 @@ __global__ void nwave_rk4_kernel(const NwaveParams p) {
         if (__syncthreads_or(nf)) bad = n_steps - 1;
     }
     if (p.status && tid == 0) p.status[b] = bad;
+#ifdef FPA_FACT_TIMING
+    if (FACT && b == 0 && tid == 0) {
+        const double per = 1.0 / (4.0 * n_steps);
+        printf("fact stage cycles (thread 0 of point 0, per stage): phases %.0f | sum+sync %.0f | classes %.0f | sync %.0f | rows %.0f | sync %.0f\n",
+               g_fact_ticks[0] * per, g_fact_ticks[1] * per, g_fact_ticks[2] * per, g_fact_ticks[3] * per,
+               g_fact_ticks[4] * per, g_fact_ticks[5] * per);
+        for (int k = 0; k < 8; ++k) g_fact_ticks[k] = 0;
+    }
+#endif
     if (p.A_end)
         for (int j = tid; j < 2 * N; j += blockDim.x) p.A_end[b * 2 * N + j] = s.y[j];
     if (p.Pmax) {
@@ -284,9 +530,15 @@ int nwave_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     FPA_REQUIRE(d->n_steps >= 1 && d->n_steps < 2147483647LL, "n_steps must be in [1, 2^31)");
     FPA_REQUIRE(d->save_every >= 1, "save_every must be a positive integer");
     FPA_REQUIRE(d->beta && d->gamma && d->alpha && d->A0, "beta/gamma/alpha/A0 must be set");
-    FPA_REQUIRE(d->n_triplets >= 0 && d->n_triplets < 2147483647LL, "bad n_triplets");
-    FPA_REQUIRE(d->row_ptr != nullptr, "row_ptr must be set");
-    FPA_REQUIRE(d->n_triplets == 0 || d->triplets, "triplets must be set");
+    // the factored form of the table (fpa_nwave_factor_table) replaces the entry list when the caller supplies it
+    const bool fact = d->factored != nullptr && !(d->flags & FPA_NWAVE_PLAIN) && getenv("FPA_NWAVE_PLAIN") == nullptr;
+    if (fact) {
+        FPA_REQUIRE(d->n_classes >= 0 && d->n_classes < kFactMaxCls, "n_classes must be the class count of `factored`");
+    } else {
+        FPA_REQUIRE(d->n_triplets >= 0 && d->n_triplets < 2147483647LL, "bad n_triplets");
+        FPA_REQUIRE(d->row_ptr != nullptr, "row_ptr must be set");
+        FPA_REQUIRE(d->n_triplets == 0 || d->triplets, "triplets must be set");
+    }
     FPA_REQUIRE((d->gamma_stride | 1) == 1 && (d->alpha_stride | 1) == 1 && (d->A0_stride | 1) == 1 &&
                     (d->beta_stride | 1) == 1,
                 "strides must be 0 (broadcast) or 1 (per point)");
@@ -323,6 +575,28 @@ int nwave_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     p.Pmax         = pmax ? d->Pmax : nullptr;
     p.status       = d->status;
     p.check        = (d->flags & FPA_CHECK_NAN) ? 1 : 0;
+    p.fact         = fact ? static_cast<const unsigned char*>(d->factored) : nullptr;
+    p.n_classes    = fact ? d->n_classes : 0;
+    p.table_in_smem = p.table_in_smem_only_one_cta = 0;
+    FPA_REQUIRE(d->n_points < 2147483647LL, "n_points too large for one launch");
+
+    if (fact) {
+        // state + class sums: 8.4 KB for N = 64 -- one CTA of 256 threads per point, several per SM
+        const size_t smem = nwave_smem_bytes(d->n_waves, 0) + (size_t)(p.n_classes + 1) * sizeof(double2);
+        if (smem <= 200 * 1024) {
+            const int   env_threads = getenv("FPA_FACT_THREADS") ? atoi(getenv("FPA_FACT_THREADS")) : 0;   // tools
+            const int   threads = env_threads >= 32 && env_threads <= 1024 ? (env_threads & ~31) : kFactThreads;
+            cudaError_t      e = cudaFuncSetAttribute(nwave_rk4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(nwave_rk4_kernel<factored>)");
+            nwave_rk4_kernel<true><<<(unsigned)d->n_points, threads, smem, st>>>(p);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "nwave_rk4_kernel<factored> launch");
+            return FPA_OK;
+        }
+        // more classes than shared memory holds: the entry list it is
+        p.fact = nullptr;
+        FPA_REQUIRE(d->row_ptr != nullptr && (d->n_triplets == 0 || d->triplets), "triplet table must be set");
+    }
 
     // the triplet list stays in shared memory when it fits beside the state (<= 200 KB in total)
     const size_t with_table = nwave_smem_bytes(d->n_waves, d->n_triplets);
@@ -340,11 +614,10 @@ int nwave_launch(const fpa_nwave_desc* d, cudaStream_t st) {
     if (d->n_points >= 4 * (int64_t)sms && !p.table_in_smem_only_one_cta) warps = warps < 8 ? warps : 8;
     const int threads = 32 * warps;
 
-    cudaError_t e = cudaFuncSetAttribute(nwave_rk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(nwave_rk4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(nwave_rk4_kernel)");
-    FPA_REQUIRE(d->n_points < 2147483647LL, "n_points too large for one launch");
-    nwave_rk4_kernel<<<(unsigned)d->n_points, threads, smem, st>>>(p);
+    nwave_rk4_kernel<false><<<(unsigned)d->n_points, threads, smem, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "nwave_rk4_kernel launch");
     return FPA_OK;
@@ -424,6 +697,178 @@ extern "C" int64_t fpa_enumerate_triplets_omega(int32_t N, const double* omega, 
     }
     if (row_ptr) row_ptr[N] = count;
     return count;
+}
+
+// ------------------------------------------------------------------ host: table factorisation
+namespace {
+struct PairW {
+    int16_t k, l;
+    int32_t w;
+    bool operator<(const PairW& o) const { return k != o.k ? k < o.k : (l != o.l ? l < o.l : w < o.w); }
+};
+struct Factored {
+    std::vector<std::vector<PairW>> classes;
+    std::vector<int>                cmap;   // [N*N] class or -1
+    std::vector<int>                wown;   // [N*N]
+    int64_t                         n_pairs = 0;
+    int                             mode = 0;
+};
+
+// groups[n*N+m] = merged, sorted (k <= l, weight) list of the entries (n; k, l, m).
+// mode 0: the groups as they are; 1: plus the own pair {n, m} of every group that has entries and lacks it;
+// 2: plus the own pair of EVERY cell -- only if no cell holds it already (then w_own is the same for all plans).
+bool factor_groups(int N, const std::vector<std::vector<PairW>>& groups, int mode, Factored* out) {
+    Factored&                         f = *out;
+    std::map<std::vector<PairW>, int> ids;
+    f = Factored();
+    f.mode = mode;
+    f.cmap.assign((size_t)N * N, -1);
+    f.wown.assign((size_t)N * N, 0);
+    for (int n = 0; n < N; ++n)
+        for (int m = 0; m < N; ++m) {
+            std::vector<PairW> key = groups[(size_t)n * N + m];
+            if (key.empty() && mode != 2) continue;
+            if (mode != 0) {
+                const PairW own = {(int16_t)(n < m ? n : m), (int16_t)(n < m ? m : n), n == m ? 1 : 2};
+                bool        present = false;
+                for (const PairW& q : key) present |= q.k == own.k && q.l == own.l;
+                if (present && mode == 2) return false;
+                if (!present) {
+                    key.insert(std::lower_bound(key.begin(), key.end(), own), own);
+                    f.wown[(size_t)n * N + m] = own.w;
+                }
+            }
+            auto it = ids.find(key);
+            if (it == ids.end()) {
+                it = ids.emplace(key, (int)f.classes.size()).first;
+                f.n_pairs += (int64_t)key.size();
+                f.classes.push_back(key);
+            }
+            f.cmap[(size_t)n * N + m] = it->second;
+        }
+    return true;
+}
+}  // namespace
+
+extern "C" int64_t fpa_nwave_factor_table(int32_t N, const fpa_triplet* triplets, const int64_t* row_ptr, int64_t n_triplets,
+                                          void* blob, int64_t cap, int32_t* n_classes) {
+    using fpa::FactHeader;
+    using fpa::FactPair;
+    if (N < 1 || N > 128 || row_ptr == nullptr || n_triplets < 0 || (n_triplets > 0 && triplets == nullptr)) {
+        fpa::set_error("fpa_nwave_factor_table: need 1 <= N <= 128 and a CSR triplet table");
+        return -1;
+    }
+    if (row_ptr[0] != 0 || row_ptr[N] != n_triplets) {
+        fpa::set_error("fpa_nwave_factor_table: row_ptr must run from 0 to n_triplets");
+        return -1;
+    }
+    std::vector<std::vector<PairW>> groups((size_t)N * N);
+    for (int n = 0; n < N; ++n) {
+        if (row_ptr[n + 1] < row_ptr[n]) {
+            fpa::set_error("fpa_nwave_factor_table: row_ptr must not decrease");
+            return -1;
+        }
+        for (int64_t e = row_ptr[n]; e < row_ptr[n + 1]; ++e) {
+            const fpa_triplet t = triplets[e];
+            if (t.k < 0 || t.k >= N || t.l < 0 || t.l >= N || t.m < 0 || t.m >= N) {
+                fpa::set_error("fpa_nwave_factor_table: entry %lld has a wave index outside [0, %d)", (long long)e, N);
+                return -1;
+            }
+            std::vector<PairW>& g = groups[(size_t)n * N + t.m];
+            const PairW         q = {t.k < t.l ? t.k : t.l, t.k < t.l ? t.l : t.k, t.weight};
+            bool                merged = false;
+            for (PairW& o : g)
+                if (o.k == q.k && o.l == q.l) {
+                    o.w += q.w;
+                    merged = true;
+                }
+            if (!merged) g.push_back(q);
+        }
+    }
+    for (auto& g : groups) {
+        std::sort(g.begin(), g.end());
+        for (const PairW& q : g)
+            if (q.w < -(1 << 24) || q.w > (1 << 24)) {      // exact in the record's float
+                fpa::set_error("fpa_nwave_factor_table: merged weight %d is out of range", q.w);
+                return -1;
+            }
+    }
+    // whichever of the three forms leaves the least to do per RHS: pair products, plus a pass over the w_own
+    // matrix for mode 1
+    Factored best, cand;
+    int64_t  best_cost = -1;
+    for (int mode = 0; mode < 3; ++mode) {
+        if (!factor_groups(N, groups, mode, &cand)) continue;
+        const int64_t cost = 6 * cand.n_pairs + (mode == 1 ? 2 * (int64_t)N * N : 0);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best      = cand;
+        }
+    }
+    Factored& f = best;
+    const int C = (int)f.classes.size();
+    if (C >= fpa::kFactMaxCls) {
+        fpa::set_error("fpa_nwave_factor_table: %d classes exceed the format's limit", C);
+        return -1;
+    }
+    // classes of similar size next to each other (four lanes work on one class, eight classes per warp)
+    std::vector<int> order((size_t)C), rank((size_t)C);
+    for (int c = 0; c < C; ++c) order[(size_t)c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return f.classes[(size_t)a].size() > f.classes[(size_t)b].size(); });
+    for (int r = 0; r < C; ++r) rank[(size_t)order[(size_t)r]] = r;
+    int64_t n_padded = 0;
+    for (const auto& c : f.classes) n_padded += ((int64_t)c.size() + 3) & ~(int64_t)3;
+
+    int lpr_log = 0;   // lanes per row: kFactThreads / N, a power of two in [1, 32]
+    while ((2 << lpr_log) * N <= fpa::kFactThreads && lpr_log < 5) ++lpr_log;
+    const int lpr = 1 << lpr_log, cpl4 = ((N + lpr - 1) / lpr + 3) & ~3;
+
+    auto       up16 = [](int64_t v) { return (v + 15) & ~(int64_t)15; };
+    FactHeader h = {};
+    h.magic      = fpa::kFactMagic;
+    h.n_waves    = N;
+    h.n_classes  = C;
+    h.n_pairs    = (int32_t)n_padded;
+    h.mode       = f.mode;
+    h.lpr_log    = lpr_log;
+    h.cpl4       = cpl4;
+    h.off_cls    = (int32_t)up16(sizeof(FactHeader));
+    h.off_pairs  = (int32_t)up16(h.off_cls + (int64_t)(C + 1) * 4);
+    h.off_cmap   = (int32_t)up16(h.off_pairs + n_padded * (int64_t)sizeof(FactPair));
+    h.off_wown   = (int32_t)up16(h.off_cmap + (int64_t)N * lpr * cpl4 * 4);
+    h.bytes      = (int32_t)up16(h.off_wown + (f.mode == 1 ? (int64_t)N * N * 2 : 0));
+    if (n_classes) *n_classes = C;
+    if (blob == nullptr || cap < h.bytes) return h.bytes;
+
+    unsigned char* base = static_cast<unsigned char*>(blob);
+    memset(base, 0, (size_t)h.bytes);
+    memcpy(base, &h, sizeof h);
+    int32_t*  cls   = reinterpret_cast<int32_t*>(base + h.off_cls);
+    FactPair* pairs = reinterpret_cast<FactPair*>(base + h.off_pairs);
+    uint32_t* cmap  = reinterpret_cast<uint32_t*>(base + h.off_cmap);
+    int16_t*  wown  = reinterpret_cast<int16_t*>(base + h.off_wown);
+    int32_t   at = 0;
+    for (int r = 0; r < C; ++r) {
+        cls[r] = at;
+        for (const PairW& q : f.classes[(size_t)order[(size_t)r]]) {
+            pairs[at].k16 = (uint16_t)(q.k * 16);
+            pairs[at].l16 = (uint16_t)(q.l * 16);
+            pairs[at].w   = (float)q.w;
+            ++at;
+        }
+        while (at & 3) pairs[at++] = FactPair{0, 0, 0.0f};     // padding: weight 0
+    }
+    cls[C] = at;
+    for (int n = 0; n < N; ++n)
+        for (int r = 0; r < lpr; ++r)
+            for (int i = 0; i < cpl4; ++i) {
+                const int m = r + lpr * i;
+                const int c = m < N ? f.cmap[(size_t)n * N + m] : -1;
+                cmap[((size_t)n * lpr + r) * cpl4 + i] = (uint32_t)(c < 0 ? C : rank[(size_t)c]) * 16u;
+            }
+    if (f.mode == 1)
+        for (size_t i = 0; i < (size_t)N * N; ++i) wown[i] = (int16_t)f.wown[i];
+    return h.bytes;
 }
 
 extern "C" double fpa_nwave_flops_per_step(int32_t n_waves, int64_t n_triplets, int64_t n_pairs) {

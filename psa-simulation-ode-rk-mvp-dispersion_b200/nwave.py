@@ -110,13 +110,13 @@ def beta_per_wave(plan: NWavePlan, disp: DispersionParams, *, max_order: int = 4
 
 def _grid_or_none(plan: NWavePlan, form: str):
     """grid indices to hand to the library: integer-grid plans use the convolution-form kernel
-    (`auto` / `comb`); `table` or an off-grid plan uses the enumerated triplets."""
-    if form not in ("auto", "comb", "table"):
-        raise ValueError("form must be 'auto', 'comb' or 'table'")
+    (`auto` / `comb`); `table` / `entries` or an off-grid plan uses the enumerated triplets."""
+    if form not in ("auto", "comb", "table", "entries"):
+        raise ValueError("form must be 'auto', 'comb', 'table' or 'entries'")
     off_grid = bool(np.all(plan.grid_index < 0)) and plan.grid_index.min() == plan.grid_index.max()
     if form == "comb" and off_grid:
         raise ValueError("the convolution form needs an integer-grid plan")
-    return None if (form == "table" or off_grid) else plan.grid_index
+    return None if (form in ("table", "entries") or off_grid) else plan.grid_index
 
 
 class NWaveRHS:
@@ -156,8 +156,9 @@ def run_nwave_simulation(cfg: SimulationConfig, plan: NWavePlan, *, gamma, alpha
     """B >= 1 N-wave runs in one launch.  Initial state from p_in/phase_in [N] or A0 [B,N];
     gamma / alpha scalars or [B]; per-wave beta from `dispersion` (per length_unit) or given
     explicitly ([N] or [B,N]).  `form`: 'auto' (the library picks: convolution form for integer-grid plans
-    within its limits unless they are sparse, else the triplet table), 'comb', 'table'.  `devices=[...]`
-    splits the points over several GPUs.  Returns dict(z, A_trace[B,n_saved,N], A_end, Pmax, status)."""
+    within its limits unless they are sparse, else the triplet table), 'comb', 'table' (the table kernel, which
+    integrates from the factored table), 'entries' (the table kernel walking the entry list: the slow,
+    independent check).  `devices=[...]` splits the points over several GPUs.  Returns dict(z, A_trace[B,n_saved,N], A_end, Pmax, status)."""
     validate_config(cfg)
     s = _length_scale_to_m(length_unit)
     N = plan.n_waves
@@ -181,8 +182,8 @@ def run_nwave_simulation(cfg: SimulationConfig, plan: NWavePlan, *, gamma, alpha
                             A0.reshape(-1, N), plan.table, plan.row_ptr, z_max=z_max, n_steps=n_steps,
                             save_every=cfg.save_every, trace="trace" in want, end="end" in want,
                             pmax="pmax" in want, check_nan=cfg.check_nan, device=device, devices=devices,
-                            grid_index=_grid_or_none(plan, form), force_table=form == "table",
-                            force_comb=form == "comb")
+                            grid_index=_grid_or_none(plan, form), force_table=form in ("table", "entries"),
+                            force_comb=form == "comb", plain_table=form == "entries")
     grid = np.linspace(0.0, z_max, n_steps + 1)
     r["z"] = np.concatenate((grid[:1], grid[cfg.save_every::cfg.save_every])) / s
     r["n_steps"] = n_steps

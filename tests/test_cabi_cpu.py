@@ -91,6 +91,113 @@ def test_off_grid_triplet_enumerator_bit_exact(fpa, nw_oracle):
         fpa.nwave.irregular_plan([1.0e15, -2.0])
 
 
+def _decode_factored(blob):
+    """The blob of `fpa_nwave_factor_table` (csrc/nwave.cu, FactHeader): class offsets, pair records
+    {k*16, l*16, float weight} padded to multiples of four per class, the cell map in lane order (byte offsets
+    into the class sums, empty cells -> slot n_classes), the own-pair weights (mode 1) -> plain arrays."""
+    h = np.frombuffer(blob[:48], dtype=np.int32)
+    assert int(h[0]) == 0x32504146
+    N, nc, n_pairs, mode, lpr_log, cpl4, o_cls, o_pairs, o_cmap, o_wown, nbytes = (int(v) for v in h[1:12])
+    assert nbytes == blob.size
+    lpr = 1 << lpr_log
+    assert lpr == max(1, min(32, 1 << int(np.floor(np.log2(256 / N))))) and cpl4 % 4 == 0 and cpl4 * lpr >= N
+    cls = np.frombuffer(blob[o_cls:o_cls + 4 * (nc + 1)], dtype=np.int32)
+    rec = np.frombuffer(blob[o_pairs:o_pairs + 8 * n_pairs], dtype=np.dtype([("k16", "<u2"), ("l16", "<u2"), ("w", "<f4")]))
+    lane = np.frombuffer(blob[o_cmap:o_cmap + 4 * N * lpr * cpl4], dtype=np.uint32).reshape(N, lpr, cpl4)
+    assert cls[0] == 0 and cls[-1] == n_pairs and np.all(np.diff(cls) >= 0) and np.all(np.diff(cls) % 4 == 0)
+    assert np.all(lane % 16 == 0) and np.all(rec["k16"] % 16 == 0) and np.all(rec["l16"] % 16 == 0)
+    cmap = np.full((N, N), nc, dtype=np.int64)
+    for r in range(lpr):
+        for i in range(cpl4):
+            m = r + lpr * i
+            if m < N:
+                cmap[:, m] = lane[:, r, i] // 16
+            else:
+                assert np.all(lane[:, r, i] == 16 * nc)        # padding cells point at the zero slot
+    if mode == 1:
+        wown = np.frombuffer(blob[o_wown:o_wown + 2 * N * N], dtype=np.int16).reshape(N, N).astype(float)
+    elif mode == 2:
+        wown = 2.0 - np.eye(N)
+    else:
+        wown = np.zeros((N, N))
+    return N, nc, cls, rec, cmap, wown, mode
+
+
+def _sum_entry_list(table, rows, A):
+    R = np.zeros(A.size, dtype=complex)
+    for n in range(A.size):
+        t = table[rows[n]:rows[n + 1]]
+        R[n] = np.sum(t["weight"] * A[t["k"]] * A[t["l"]] * np.conj(A[t["m"]]))
+    return R
+
+
+def _sum_factored(blob, A):
+    N, nc, cls, rec, cmap, wown, _ = _decode_factored(blob)
+    prod = rec["w"].astype(float) * A[rec["k16"] // 16] * A[rec["l16"] // 16]
+    T = np.array([prod[cls[c]:cls[c + 1]].sum() for c in range(nc)] + [0.0])
+    return (T[cmap] * np.conj(A)[None, :]).sum(axis=1) - A * (wown * np.abs(A)[None, :] ** 2).sum(axis=1)
+
+
+@pytest.mark.parametrize("case", ["comb64", "gapped", "offgrid", "fixed4", "ragged", "empty"])
+def test_factored_table_is_the_same_sum(fpa, case):
+    """`fpa_nwave_factor_table`: whatever the table, the factored form sums to the entry list's triplet sums."""
+    dev = fpa._device
+    rng = np.random.default_rng(5)
+    if case == "comb64":
+        N = 64
+        table, rows = dev.enumerate_triplets(np.arange(N))
+    elif case == "gapped":
+        g = np.array([-9, -4, -3, 0, 1, 2, 5, 11, 12])
+        N = g.size
+        table, rows = dev.enumerate_triplets(g)
+    elif case == "offgrid":
+        w0 = 1.2e15
+        w = w0 + 2 * np.pi * 1e11 * np.array([-3.0, -2.0, -1.0, 0.0, 1.0, 2.0, 3.0, 0.5, 1.5, 4.37])
+        N = w.size
+        table, rows = dev.enumerate_triplets_omega(w)
+    elif case == "fixed4":
+        N = 4
+        table = np.array([(2, 3, 1, 2), (2, 3, 0, 2), (0, 1, 3, 2), (0, 1, 2, 2)], dtype=fpa._lib.TRIPLET_DTYPE)
+        rows = np.arange(5, dtype=np.int64)
+    elif case == "ragged":      # nothing a frequency plan would give: repeats, k > l, odd weights, empty rows
+        N = 7
+        ent = [(0, 3, 2, 1, 5), (0, 2, 3, 1, -2), (0, 1, 1, 0, 3), (0, 6, 6, 0, 1), (2, 5, 4, 2, 7), (2, 0, 1, 3, 1), (6, 0, 0, 0, 1)]
+        table = np.array([e[1:] for e in ent], dtype=fpa._lib.TRIPLET_DTYPE)
+        rows = np.searchsorted(np.array([e[0] for e in ent]), np.arange(N + 1)).astype(np.int64)
+    else:
+        N = 5
+        table = np.empty(0, dtype=fpa._lib.TRIPLET_DTYPE)
+        rows = np.zeros(N + 1, dtype=np.int64)
+    blob, nc = dev.factor_table(N, table, rows)
+    dN, dnc, cls, pairs, cmap, wown, mode = _decode_factored(blob)
+    assert (dN, dnc) == (N, nc)
+    A = rng.normal(size=N) + 1j * rng.normal(size=N)
+    want, got = _sum_entry_list(table, rows, A), _sum_factored(blob, A)
+    scale = max(1.0, float(np.abs(A).max()) ** 3 * max(1, table.size))
+    assert np.abs(got - want).max() <= 1e-13 * scale
+    live = int((pairs["w"] != 0).sum())
+    if case == "comb64":        # one class per sum frequency, every pair product formed once; own pairs in every
+        # cell, so the correction is (2S - P_n) At_n and needs no matrix
+        assert mode == 2 and nc == 2 * N - 1 and live == N * (N + 1) // 2 and table.size == 84320
+        assert np.all(np.diff(np.diff(cls)) <= 0)      # classes of similar size next to each other
+    if case == "fixed4":        # the reference's four-process table: two pair products, nothing added
+        assert mode == 0 and nc == 2 and live == 2
+    if case == "empty":
+        assert nc == 0 and pairs.size == 0 and np.all(cmap == nc) and mode == 0
+
+
+def test_factor_table_rejects_malformed_input(fpa):
+    L = fpa._lib.lib()
+    nc = C.c_int32()
+    rows = np.array([0, 1, 1], dtype=np.int64)
+    bad = np.array([(0, 5, 1, 2)], dtype=fpa._lib.TRIPLET_DTYPE)      # l = 5 with N = 2
+    assert L.fpa_nwave_factor_table(2, fpa._device.ptr(bad), fpa._device.ptr(rows), 1, None, 0, C.byref(nc)) == -1
+    assert "outside" in fpa._lib.last_error()
+    assert L.fpa_nwave_factor_table(200, fpa._device.ptr(bad), fpa._device.ptr(rows), 1, None, 0, C.byref(nc)) == -1
+    rows2 = np.array([0, 2, 1], dtype=np.int64)
+    assert L.fpa_nwave_factor_table(2, fpa._device.ptr(bad), fpa._device.ptr(rows2), 1, None, 0, C.byref(nc)) == -1
+
+
 def test_no_cpu_fallback(fpa):
     """Without a device every compute call raises; with one this test is skipped."""
     if fpa._lib.device_count() > 0:

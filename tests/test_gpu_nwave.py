@@ -143,8 +143,6 @@ def test_comb_equals_table_on_odd_shapes(gpu, lines, batch):
     nw = gpu.nwave
     plan = nw.uniform_comb_plan(1.2125e15, 6.28e11, lines)
     N = plan.n_waves
-    if N > 48 and batch > 2:
-        pytest.skip("table kernel at N > 48 and 640 points: minutes")
     disp = gpu.dispersion.DispersionParams(1.2125e15, beta2=-2.6e-29, beta3=3.3e-41, beta4=-1.6e-55)
     beta = nw.beta_per_wave(plan, disp)
     rng = np.random.default_rng(N + batch)
@@ -156,6 +154,85 @@ def test_comb_equals_table_on_odd_shapes(gpu, lines, batch):
     assert np.max(np.abs(t["A_end"] - c["A_end"])) < 1e-12 * scale
     assert np.max(np.abs(t["Pmax"] - c["Pmax"])) < 1e-12 * scale ** 2
     assert (c["status"] == -1).all()
+    if N <= 48 or batch == 2:       # and the table kernel's two ways through the table (entry list: minutes beyond)
+        e = nw.run_nwave_simulation(cfg, plan, gamma=0.02, alpha=1e-4, A0=A0, beta=beta, form="entries", outputs=("end", "pmax"))
+        assert np.max(np.abs(t["A_end"] - e["A_end"])) < 1e-13 * scale
+        assert np.max(np.abs(t["Pmax"] - e["Pmax"])) < 1e-13 * scale ** 2
+
+
+def test_factored_table_equals_entry_list(gpu, nw_oracle):
+    """The table kernel integrates from `fpa_nwave_factor_table`'s form of the table (pair products once per RHS);
+    FPA_NWAVE_PLAIN walks the entry list as round 1 did.  Same ODE, different summation order: 1e-13 of the
+    state's scale -- on tables from plans (comb, off-grid, the reference's fixed four-wave table) and on one no
+    plan would give (repeats, k > l, negative weights, empty rows), the latter against the oracle's march too."""
+    nw, D = gpu.nwave, gpu._device
+    rng = np.random.default_rng(11)
+    w0, dw = 1.2125e15, 6.28e11
+    disp = gpu.dispersion.DispersionParams(w0, beta2=-2.6e-29, beta3=3.3e-41, beta4=-1.6e-55)
+    cases = []
+    for lines in (range(-10, 11), range(-32, 32)):
+        plan = nw.uniform_comb_plan(w0, dw, lines)
+        cases.append((plan.n_waves, plan.table, plan.row_ptr, nw.beta_per_wave(plan, disp)))
+    off = nw.irregular_plan(w0 + dw * np.array([-5.0, 5.0, 1.3, -1.3, 2.77, -7.41, 0.0, 3.7, -3.7]))
+    cases.append((off.n_waves, off.table, off.row_ptr, nw.beta_per_wave(off, disp)))
+    ent = [(0, 3, 2, 1, 5), (0, 2, 3, 1, -2), (0, 1, 1, 0, 3), (0, 6, 6, 0, 1), (2, 5, 4, 2, 7), (2, 0, 1, 3, 1), (6, 0, 0, 0, 1)]
+    ragged = np.array([e[1:] for e in ent], dtype=gpu._lib.TRIPLET_DTYPE)
+    rrows = np.searchsorted(np.array([e[0] for e in ent]), np.arange(8)).astype(np.int64)
+    cases.append((7, ragged, rrows, rng.uniform(-2.0, 2.0, 7)))
+    for N, table, rows, beta in cases:
+        B = 3
+        A0 = np.sqrt(rng.uniform(1e-4, 0.3, (B, N))) * np.exp(1j * rng.uniform(0, 6.28, (B, N)))
+        kw = dict(z_max=6.0, n_steps=60, save_every=7, trace=True, end=True, pmax=True, force_table=True)
+        f = D.nwave_batch(beta, 0.02, 1e-4, A0, table, rows, **kw)
+        e = D.nwave_batch(beta, 0.02, 1e-4, A0, table, rows, plain_table=True, **kw)
+        scale = np.abs(e["A_trace"]).max()
+        assert (f["status"] == -1).all() and (e["status"] == -1).all()
+        for key, pw in (("A_trace", 1), ("A_end", 1), ("Pmax", 2)):
+            assert np.max(np.abs(f[key] - e[key])) < 1e-13 * scale ** pw, (N, key)
+    # the ragged table against the CPU march
+    N, table, rows, beta = cases[-1]
+    A0 = np.sqrt(rng.uniform(1e-4, 0.3, N)) * np.exp(1j * rng.uniform(0, 6.28, N))
+    f = D.nwave_batch(beta, 0.02, 1e-4, A0[None, :], table, rows, z_max=6.0, n_steps=60, save_every=6, trace=True, force_table=True)
+    tl = [(int(a), int(b), int(c), int(d)) for a, b, c, d in zip(table["k"], table["l"], table["m"], table["weight"])]
+    _, A_ref = nw_oracle.march(A0, 0.02, 1e-4, beta, tl, rrows.tolist(), z_max=6.0, n_steps=60, save_every=6)
+    assert np.max(np.abs(f["A_trace"][0] - A_ref)) < 1e-12 * np.max(np.abs(A_ref))
+
+
+def test_foreign_factored_blob_gives_no_result(gpu):
+    """`_dev` callers pass the blob themselves: one that does not belong to the plan (wrong class count / wave
+    count) must not produce numbers -- status 0 and NaN."""
+    import ctypes as C
+
+    import torch
+    L, lib, D = gpu._lib, gpu._lib.lib(), gpu._device
+    dev = torch.device("cuda", 0)
+    table, rows = D.enumerate_triplets(np.arange(8))
+    blob, nc = D.factor_table(8, table, rows)
+    t_blob = torch.from_numpy(blob).to(dev)
+    t_A0 = torch.ones(16, dtype=torch.float64, device=dev)
+    t_beta = torch.zeros(8, dtype=torch.float64, device=dev)
+    t_ga = torch.tensor([0.01, 0.0], dtype=torch.float64, device=dev)
+    t_out = torch.zeros(16, dtype=torch.float64, device=dev)
+    t_st = torch.full((1,), 7, dtype=torch.int32, device=dev)
+    d = L.NwaveDesc()
+    d.n_points, d.n_waves = 1, 8
+    d.beta, d.gamma, d.alpha, d.A0 = t_beta.data_ptr(), t_ga.data_ptr(), t_ga.data_ptr() + 8, t_A0.data_ptr()
+    d.z0, d.z_max, d.n_steps, d.save_every = 0.0, 1.0, 10, 1
+    d.flags = L.OUT_END | L.CHECK_NAN | L.NWAVE_TABLE
+    d.A_end, d.status = t_out.data_ptr(), t_st.data_ptr()
+    d.factored, d.n_classes = t_blob.data_ptr(), nc          # triplets / row_ptr left NULL: the blob is enough
+    L.check(lib.fpa_nwave_rk4_batch_dev(C.byref(d), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(t_st[0]) == -1 and bool(torch.isfinite(t_out).all())
+    good = t_out.clone()
+    d.n_classes = nc + 1
+    L.check(lib.fpa_nwave_rk4_batch_dev(C.byref(d), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(t_st[0]) == 0 and bool(torch.isnan(t_out).all())
+    d.n_classes = nc
+    L.check(lib.fpa_nwave_rk4_batch_dev(C.byref(d), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(t_out, good)
 
 
 

@@ -23,10 +23,17 @@ for r in rows:
         continue
     key = (fname, int(r[0]))
     a = agg[key]
-    a[0] += int(r[col["Instructions Executed"]] or 0)
-    a[1] += int(r[col["# Samples"]] or 0)
-    a[2] += int(r[col["L1 Wavefronts Shared"]] or 0)
-    a[3] += int(r[col["L1 Wavefronts Shared Excessive"]] or 0)
+
+    def num(name):
+        v = r[col[name]].replace(",", "").split("(")[0]
+        try:
+            return int(float(v)) if v not in ("", "-") else 0
+        except ValueError:      # a source line with commas / quotes of its own shifted the columns
+            return 0
+    a[0] += num("Instructions Executed")
+    a[1] += num("# Samples")
+    a[2] += num("L1 Wavefronts Shared")
+    a[3] += num("L1 Wavefronts Shared Excessive")
     a[4] = r[1].strip()[:90]
 tot_i = sum(a[0] for a in agg.values()) or 1
 tot_s = sum(a[1] for a in agg.values()) or 1
