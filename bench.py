@@ -809,17 +809,24 @@ def run_secondary(fpa, torch, dev, local, disp4, peak_tf, t_flush) -> dict:
         d.alpha, d.alpha_stride = t_ga.data_ptr() + 8, 0
         d.A0, d.A0_stride = t_A0.data_ptr(), 1
         d.z0, d.z_max, d.n_steps, d.save_every = 0.0, z_max, n_steps, save_every
-        d.flags = (L.OUT_TRACE if trace else L.OUT_END) | L.CHECK_NAN | (L.NWAVE_TABLE if form == "table" else 0)
+        d.flags = (L.OUT_TRACE if trace else L.OUT_END) | L.CHECK_NAN | (L.NWAVE_TABLE if form in ("table", "entries") else 0)
         if trace:
             d.A_trace = t_out.data_ptr()
         else:
             d.A_end = t_out.data_ptr()
         d.status = t_st.data_ptr()
-        if form == "table":
+        if form in ("table", "entries"):
             t_tab = torch.from_numpy(plan.table.view(np.int16).copy()).to(dev)
             t_rows = torch.from_numpy(plan.row_ptr.copy()).to(dev)
             keep += [t_tab, t_rows]
             d.triplets, d.row_ptr, d.n_triplets = t_tab.data_ptr(), t_rows.data_ptr(), plan.n_triplets
+            if form == "table":     # the table kernel integrates from the factored table; "entries": the entry list
+                blob, n_classes = fpa._device.factor_table(N, plan.table, plan.row_ptr)
+                t_blob = torch.from_numpy(blob).to(dev)
+                keep.append(t_blob)
+                d.factored, d.n_classes = t_blob.data_ptr(), n_classes
+            else:
+                d.flags |= L.NWAVE_PLAIN
         else:
             g = plan.grid_index.astype(np.int64)
             t_slot = torch.from_numpy((g - g.min()).astype(np.int32)).to(dev)
@@ -856,12 +863,12 @@ def run_secondary(fpa, torch, dev, local, disp4, peak_tf, t_flush) -> dict:
             A0n[b] = np.sqrt(p) * np.exp(1j * phases)
         return A0n
 
-    for Bn, form, steps in ((1, "comb", 100_000), (1024, "comb", 100_000), (148, "table", 2_000)):
+    for Bn, form, steps in ((1, "comb", 100_000), (1024, "comb", 100_000), (148, "table", 2_000), (148, "entries", 400)):
         d, keep = nwave_dev(plan64, beta64, comb_A0(Bn), 11.5e-3, 2e-4, 1e4 * steps / 1e5, steps, 100, form, False)
         ms = timed(lambda: L.check(lib.fpa_nwave_rk4_batch_dev(C.byref(d), stream())), reps=1 if steps > 10_000 else 3)
         res[f"config5_n64_B{Bn}_{form}"] = entry(Bn, steps, ms, plan64.flops_per_step(form), waves=64,
                                                  note="N > 4: oracle parity unpinned (no reference exists)" +
-                                                      ("" if steps == 100_000 else "; 2 000 of the 1e5 steps (rate is constant in z)"))
+                                                      ("" if steps == 100_000 else f"; {steps} of the 1e5 steps (rate is constant in z)"))
     return res
 
 

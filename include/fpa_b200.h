@@ -340,6 +340,9 @@ int fpa_nwave_rk4_batch_host(const fpa_nwave_desc* d, int device);
 int fpa_nwave_rk4_batch_multi_host(const fpa_nwave_desc* d, int n_devices, const int* devices);
 /* Algorithmic flops per point.step the N-wave kernel is credited with. */
 double fpa_nwave_flops_per_step(int32_t n_waves, int64_t n_triplets, int64_t n_pairs);
+/* Same for the table kernel integrating from a factored table (`blob`: the HOST copy fpa_nwave_factor_table
+ * wrote): 8 per non-empty cell, 10 per pair product, 30 N per RHS; 0 for a foreign blob. */
+double fpa_nwave_factored_flops_per_step(const void* blob);
 /* Same for the convolution-form kernel (O(span^2) work: credited with what it executes). */
 double fpa_nwave_comb_flops_per_step(int32_t n_waves, int32_t grid_span);
 

@@ -133,6 +133,7 @@ SIGNATURES = {
     "fpa_nwave_rk4_batch_dev": (C.c_int, [C.POINTER(NwaveDesc), C.c_void_p]),
     "fpa_nwave_rk4_batch_host": (C.c_int, [C.POINTER(NwaveDesc), C.c_int]),
     "fpa_nwave_flops_per_step": (C.c_double, [C.c_int32, C.c_int64, C.c_int64]),
+    "fpa_nwave_factored_flops_per_step": (C.c_double, [C.c_void_p]),
     "fpa_nwave_comb_flops_per_step": (C.c_double, [C.c_int32, C.c_int32]),
     "fpa_fp64_peak_probe": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp]),
     "fpa_yaman4_flops_per_step": (C.c_double, []),

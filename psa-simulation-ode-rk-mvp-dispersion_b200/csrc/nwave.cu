@@ -62,12 +62,16 @@ struct NwaveParams {
 // per cell); nothing about the plan is assumed.  Modes: 0 no own pairs (w_own = 0); 1 own pairs where a group
 // has entries, w_own matrix; 2 own pairs in EVERY cell, so sum_m w_own P_m = 2 S - P_n needs no matrix.
 //
-// Layout for the kernel: pair records {k*16, l*16, weight} with every class padded to a multiple of 4 (weight 0);
-// the cell map in LANE ORDER -- row n is shared by lpr = 2^lpr_log lanes, lane r takes m = r, r + lpr, ... and
-// its cells are contiguous, four byte offsets into T per 16-byte load (empty cells point at a zero slot T[C]).
+// Layout for the kernel: pair records {k*16, l*16, weight}, classes in order of falling size (lanes that work side
+// by side get lists of similar length) with every class padded to a multiple of 4 (weight 0); cls[c] = {first
+// pair, byte offset of the class sum's slot in T} -- the slots are numbered in order of first appearance in the
+// cell map, which for a comb is the order of the sum frequency, so the lanes of a row read neighbouring slots;
+// the cell map holds for every row n the byte offsets into T of its N_pad = 2^np_log cells (empty and padding
+// cells point at a zero slot T[C]) in BIT-REVERSED order of m: the cells m = r (mod L) are then contiguous for
+// every power of two L, so whatever number of lanes shares a row, each lane reads its cells with 16-byte loads.
 struct FactHeader {
     uint32_t magic;
-    int32_t  n_waves, n_classes, n_pairs, mode, lpr_log, cpl4;
+    int32_t  n_waves, n_classes, n_pairs, mode, np_log, reserved;
     int32_t  off_cls, off_pairs, off_cmap, off_wown;   // bytes from the start of the blob
     int32_t  bytes;
 };
@@ -75,9 +79,9 @@ struct FactPair {
     uint16_t k16, l16;   // byte offsets of At_k, At_l (index * 16)
     float    w;
 };
-constexpr uint32_t kFactMagic   = 0x32504146u;   // "FAP2"
+constexpr uint32_t kFactMagic   = 0x33504146u;   // "FAP3"
 constexpr int      kFactMaxCls  = 1 << 20;
-constexpr int      kFactThreads = 256;           // lanes per row = kFactThreads / N (a power of two, 1..32)
+constexpr int      kFactThreads = 256;           // per point; 512 when the batch leaves SMs to spare
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -212,25 +216,30 @@ __device__ long long g_fact_ticks[8];
 #endif
 
 struct FactView {
-    const int32_t*  cls;
+    const int2*     cls;
     const FactPair* pairs;
     const uint32_t* cmap;
     const int16_t*  wown;
-    int             C, mode, lpr_log, cpl4, ok;
+    int             C, mode, np_log, lpr_log, lpc_log, ok;
 };
 
 __device__ __forceinline__ FactView fact_view(const NwaveParams& p) {
     const FactHeader* h = reinterpret_cast<const FactHeader*>(p.fact);
     FactView          f;
-    f.ok      = h->magic == kFactMagic && h->n_waves == p.n_waves && h->n_classes == p.n_classes;
-    f.cls     = reinterpret_cast<const int32_t*>(p.fact + h->off_cls);
-    f.pairs   = reinterpret_cast<const FactPair*>(p.fact + h->off_pairs);
-    f.cmap    = reinterpret_cast<const uint32_t*>(p.fact + h->off_cmap);
-    f.wown    = reinterpret_cast<const int16_t*>(p.fact + h->off_wown);
-    f.C       = h->n_classes;
-    f.mode    = h->mode;
-    f.lpr_log = h->lpr_log;
-    f.cpl4    = h->cpl4;
+    f.ok     = h->magic == kFactMagic && h->n_waves == p.n_waves && h->n_classes == p.n_classes;
+    f.cls    = reinterpret_cast<const int2*>(p.fact + h->off_cls);
+    f.pairs  = reinterpret_cast<const FactPair*>(p.fact + h->off_pairs);
+    f.cmap   = reinterpret_cast<const uint32_t*>(p.fact + h->off_cmap);
+    f.wown   = reinterpret_cast<const int16_t*>(p.fact + h->off_wown);
+    f.C      = h->n_classes;
+    f.mode   = h->mode;
+    f.np_log = h->np_log;
+    // lanes per row: as many as the CTA has for N_pad rows, at least four cells per lane (one 16-byte load)
+    const int t_log = 31 - __clz((int)blockDim.x);
+    f.lpr_log = max(0, min(min(5, f.np_log - 2), t_log - f.np_log));
+    // lanes per class: 4, more when the CTA has lanes to spare for all classes at once
+    f.lpc_log = 2;
+    while (f.lpc_log < 5 && (f.C << (f.lpc_log + 1)) <= (int)blockDim.x) ++f.lpc_log;
     return f;
 }
 
@@ -273,8 +282,8 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
     if (nwarps & 1) S += s.red[nwarps - 1];
     S += S1;
 
-    // class sums T_c: four lanes per class, every class a multiple of four pairs; two pairs of a lane in flight
-    const int sub4 = tid & 3;
+    // class sums T_c: lpc lanes per class, two pairs of a lane in flight
+    const int lpc_log = f.lpc_log, lpc = 1 << lpc_log, csub = tid & (lpc - 1);
     auto      pair_term = [&](const uint2 u, double& qr, double& qi) {
         const double2 a = *reinterpret_cast<const double2*>(Atb + (u.x & 0xFFFFu));
         const double2 b = *reinterpret_cast<const double2*>(Atb + (u.x >> 16));
@@ -284,15 +293,18 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
         qr = fma(w, pr, qr);
         qi = fma(w, pi, qi);
     };
-    for (int base = 0; base < f.C; base += (int)(blockDim.x >> 2)) {
-        const int c = base + (tid >> 2);
+    for (int base = 0; base < f.C; base += (int)(blockDim.x >> lpc_log)) {
+        const int c = base + (tid >> lpc_log);
         double    qr = 0.0, qi = 0.0, q2 = 0.0, j2 = 0.0;
+        int       slot = 0;
         if (c < f.C) {
             const uint2* pp = reinterpret_cast<const uint2*>(f.pairs);
-            const int    e1 = __ldg(f.cls + c + 1);
-            int          e = __ldg(f.cls + c) + sub4;
-            for (; e + 4 < e1; e += 8) {
-                const uint2 u0 = __ldg(pp + e), u1 = __ldg(pp + e + 4);
+            const int2   c0 = __ldg(f.cls + c);
+            const int    e1 = __ldg(f.cls + c + 1).x;
+            int          e = c0.x + csub;
+            slot           = c0.y;
+            for (; e + lpc < e1; e += 2 * lpc) {
+                const uint2 u0 = __ldg(pp + e), u1 = __ldg(pp + e + lpc);
                 pair_term(u0, qr, qi);
                 pair_term(u1, q2, j2);
             }
@@ -300,42 +312,55 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
             qr += q2;
             qi += j2;
         }
-        qr += __shfl_xor_sync(0xffffffffu, qr, 1);
-        qi += __shfl_xor_sync(0xffffffffu, qi, 1);
-        qr += __shfl_xor_sync(0xffffffffu, qr, 2);
-        qi += __shfl_xor_sync(0xffffffffu, qi, 2);
-        if (c < f.C && sub4 == 0) s.T[c] = make_double2(qr, qi);
+        for (int o = lpc >> 1; o > 0; o >>= 1) {
+            qr += __shfl_xor_sync(0xffffffffu, qr, o);
+            qi += __shfl_xor_sync(0xffffffffu, qi, o);
+        }
+        if (c < f.C && csub == 0) *reinterpret_cast<double2*>(const_cast<unsigned char*>(Tb) + slot) = make_double2(qr, qi);
     }
     FPA_FTICK(2);
     __syncthreads();
     FPA_FTICK(3);
 
-    // rows: lpr lanes per row, four cells per 16-byte load of the lane-ordered map; cells beyond N point at the
-    // zero slot (their At index is clamped), so the body has no branches and its eight loads go out together
+    // rows: lpr lanes per row; a lane's cells are one contiguous run of the bit-reversed map, four per 16-byte
+    // load; cells beyond N point at the zero slot (their At index is clamped), so the body has no branches and its
+    // eight shared-memory loads go out together
     const int lpr_log = f.lpr_log, lpr = 1 << lpr_log, rsub = tid & (lpr - 1);
+    const int cpl = 1 << (f.np_log - lpr_log), rev_shift = 32 - f.np_log;
     for (int base = 0; base < N; base += (int)(blockDim.x >> lpr_log)) {
         const int n = base + (tid >> lpr_log);
         double    rr = 0.0, ri = 0.0, r2 = 0.0, i2 = 0.0, r3 = 0.0, i3 = 0.0, r4 = 0.0, i4 = 0.0, cw = 0.0;
         if (n < N) {
-            const uint4* cm = reinterpret_cast<const uint4*>(f.cmap + ((size_t)n * lpr + rsub) * f.cpl4);
-            uint4        o = __ldg(cm);
-            for (int i = 0, m = rsub; i < f.cpl4; i += 4, m += 4 * lpr) {
-                const uint4   on = __ldg(cm + (i + 4 < f.cpl4 ? (i >> 2) + 1 : 0));
-                const double2 t0 = *reinterpret_cast<const double2*>(Tb + o.x);
-                const double2 t1 = *reinterpret_cast<const double2*>(Tb + o.y);
-                const double2 t2 = *reinterpret_cast<const double2*>(Tb + o.z);
-                const double2 t3 = *reinterpret_cast<const double2*>(Tb + o.w);
-                const double2 b0 = At2[min(m, N - 1)], b1 = At2[min(m + lpr, N - 1)];
-                const double2 b2 = At2[min(m + 2 * lpr, N - 1)], b3 = At2[min(m + 3 * lpr, N - 1)];
-                rr = fma(t0.x, b0.x, fma(t0.y, b0.y, rr));   // T * conj(At_m)
-                ri = fma(t0.y, b0.x, fma(-t0.x, b0.y, ri));
-                r2 = fma(t1.x, b1.x, fma(t1.y, b1.y, r2));
-                i2 = fma(t1.y, b1.x, fma(-t1.x, b1.y, i2));
-                r3 = fma(t2.x, b2.x, fma(t2.y, b2.y, r3));
-                i3 = fma(t2.y, b2.x, fma(-t2.x, b2.y, i3));
-                r4 = fma(t3.x, b3.x, fma(t3.y, b3.y, r4));
-                i4 = fma(t3.y, b3.x, fma(-t3.x, b3.y, i4));
-                o = on;
+            const int    q0 = rsub * cpl;
+            const uint4* cm = reinterpret_cast<const uint4*>(f.cmap + ((size_t)n << f.np_log) + q0);
+            auto         wave_of = [&](int q) { return min((int)(__brev((unsigned)q) >> rev_shift), N - 1); };
+            if (cpl >= 4) {
+                uint4 o = __ldg(cm);
+                for (int i = 0; i < cpl; i += 4) {
+                    const uint4   on = __ldg(cm + (i + 4 < cpl ? (i >> 2) + 1 : 0));
+                    const double2 t0 = *reinterpret_cast<const double2*>(Tb + o.x);
+                    const double2 t1 = *reinterpret_cast<const double2*>(Tb + o.y);
+                    const double2 t2 = *reinterpret_cast<const double2*>(Tb + o.z);
+                    const double2 t3 = *reinterpret_cast<const double2*>(Tb + o.w);
+                    const double2 b0 = At2[wave_of(q0 + i)], b1 = At2[wave_of(q0 + i + 1)];
+                    const double2 b2 = At2[wave_of(q0 + i + 2)], b3 = At2[wave_of(q0 + i + 3)];
+                    rr = fma(t0.x, b0.x, fma(t0.y, b0.y, rr));   // T * conj(At_m)
+                    ri = fma(t0.y, b0.x, fma(-t0.x, b0.y, ri));
+                    r2 = fma(t1.x, b1.x, fma(t1.y, b1.y, r2));
+                    i2 = fma(t1.y, b1.x, fma(-t1.x, b1.y, i2));
+                    r3 = fma(t2.x, b2.x, fma(t2.y, b2.y, r3));
+                    i3 = fma(t2.y, b2.x, fma(-t2.x, b2.y, i3));
+                    r4 = fma(t3.x, b3.x, fma(t3.y, b3.y, r4));
+                    i4 = fma(t3.y, b3.x, fma(-t3.x, b3.y, i4));
+                    o = on;
+                }
+            } else {      // N_pad < 4: one lane, one to two cells
+                for (int i = 0; i < cpl; ++i) {
+                    const double2 t0 = *reinterpret_cast<const double2*>(Tb + __ldg(f.cmap + ((size_t)n << f.np_log) + q0 + i));
+                    const double2 b0 = At2[wave_of(q0 + i)];
+                    rr = fma(t0.x, b0.x, fma(t0.y, b0.y, rr));
+                    ri = fma(t0.y, b0.x, fma(-t0.x, b0.y, ri));
+                }
             }
             rr = (rr + r2) + (r3 + r4);
             ri = (ri + i2) + (i3 + i4);
@@ -380,7 +405,7 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
 }
 
 template <bool FACT>
-__global__ void nwave_rk4_kernel(const NwaveParams p) {
+__global__ void __launch_bounds__(1024) nwave_rk4_kernel(const NwaveParams p) {
     extern __shared__ double smem_raw[];
     const int     N = p.n_waves;
     const int64_t b = blockIdx.x;
@@ -584,8 +609,15 @@ int nwave_launch(const fpa_nwave_desc* d, cudaStream_t st) {
         // state + class sums: 8.4 KB for N = 64 -- one CTA of 256 threads per point, several per SM
         const size_t smem = nwave_smem_bytes(d->n_waves, 0) + (size_t)(p.n_classes + 1) * sizeof(double2);
         if (smem <= 200 * 1024) {
-            const int   env_threads = getenv("FPA_FACT_THREADS") ? atoi(getenv("FPA_FACT_THREADS")) : 0;   // tools
-            const int   threads = env_threads >= 32 && env_threads <= 1024 ? (env_threads & ~31) : kFactThreads;
+            // a batch that leaves SMs to spare gets 512 threads per point (a single run is one CTA whatever its size:
+            // the latencies of its passes are all there is to hide; 1024 threads cost more in instructions issued
+            // by lanes without work than they hide); FPA_FACT_THREADS overrides (tools)
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int env_threads = getenv("FPA_FACT_THREADS") ? atoi(getenv("FPA_FACT_THREADS")) : 0;
+            int       threads = d->n_points <= 2 * (int64_t)sms ? 512 : kFactThreads;
+            if (env_threads >= 32 && env_threads <= 1024) threads = env_threads & ~31;
             cudaError_t      e = cudaFuncSetAttribute(nwave_rk4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(nwave_rk4_kernel<factored>)");
             nwave_rk4_kernel<true><<<(unsigned)d->n_points, threads, smem, st>>>(p);
@@ -811,17 +843,20 @@ extern "C" int64_t fpa_nwave_factor_table(int32_t N, const fpa_triplet* triplets
         fpa::set_error("fpa_nwave_factor_table: %d classes exceed the format's limit", C);
         return -1;
     }
-    // classes of similar size next to each other (four lanes work on one class, eight classes per warp)
-    std::vector<int> order((size_t)C), rank((size_t)C);
+    // processing order: classes of similar size next to each other (lanes that work side by side); slot order:
+    // first appearance in the row-major cell map
+    std::vector<int> order((size_t)C), slot((size_t)C, -1);
     for (int c = 0; c < C; ++c) order[(size_t)c] = c;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return f.classes[(size_t)a].size() > f.classes[(size_t)b].size(); });
-    for (int r = 0; r < C; ++r) rank[(size_t)order[(size_t)r]] = r;
+    int n_slots = 0;
+    for (size_t i = 0; i < (size_t)N * N; ++i)
+        if (f.cmap[i] >= 0 && slot[(size_t)f.cmap[i]] < 0) slot[(size_t)f.cmap[i]] = n_slots++;
     int64_t n_padded = 0;
     for (const auto& c : f.classes) n_padded += ((int64_t)c.size() + 3) & ~(int64_t)3;
 
-    int lpr_log = 0;   // lanes per row: kFactThreads / N, a power of two in [1, 32]
-    while ((2 << lpr_log) * N <= fpa::kFactThreads && lpr_log < 5) ++lpr_log;
-    const int lpr = 1 << lpr_log, cpl4 = ((N + lpr - 1) / lpr + 3) & ~3;
+    int np_log = 0;
+    while ((1 << np_log) < N) ++np_log;
+    const int n_pad = 1 << np_log;
 
     auto       up16 = [](int64_t v) { return (v + 15) & ~(int64_t)15; };
     FactHeader h = {};
@@ -830,12 +865,11 @@ extern "C" int64_t fpa_nwave_factor_table(int32_t N, const fpa_triplet* triplets
     h.n_classes  = C;
     h.n_pairs    = (int32_t)n_padded;
     h.mode       = f.mode;
-    h.lpr_log    = lpr_log;
-    h.cpl4       = cpl4;
+    h.np_log     = np_log;
     h.off_cls    = (int32_t)up16(sizeof(FactHeader));
-    h.off_pairs  = (int32_t)up16(h.off_cls + (int64_t)(C + 1) * 4);
+    h.off_pairs  = (int32_t)up16(h.off_cls + (int64_t)(C + 1) * 8);
     h.off_cmap   = (int32_t)up16(h.off_pairs + n_padded * (int64_t)sizeof(FactPair));
-    h.off_wown   = (int32_t)up16(h.off_cmap + (int64_t)N * lpr * cpl4 * 4);
+    h.off_wown   = (int32_t)up16(h.off_cmap + (int64_t)N * n_pad * 4);
     h.bytes      = (int32_t)up16(h.off_wown + (f.mode == 1 ? (int64_t)N * N * 2 : 0));
     if (n_classes) *n_classes = C;
     if (blob == nullptr || cap < h.bytes) return h.bytes;
@@ -843,14 +877,16 @@ extern "C" int64_t fpa_nwave_factor_table(int32_t N, const fpa_triplet* triplets
     unsigned char* base = static_cast<unsigned char*>(blob);
     memset(base, 0, (size_t)h.bytes);
     memcpy(base, &h, sizeof h);
-    int32_t*  cls   = reinterpret_cast<int32_t*>(base + h.off_cls);
+    int32_t*  cls   = reinterpret_cast<int32_t*>(base + h.off_cls);      // {first pair, slot byte offset} per class
     FactPair* pairs = reinterpret_cast<FactPair*>(base + h.off_pairs);
     uint32_t* cmap  = reinterpret_cast<uint32_t*>(base + h.off_cmap);
     int16_t*  wown  = reinterpret_cast<int16_t*>(base + h.off_wown);
     int32_t   at = 0;
     for (int r = 0; r < C; ++r) {
-        cls[r] = at;
-        for (const PairW& q : f.classes[(size_t)order[(size_t)r]]) {
+        const int c    = order[(size_t)r];
+        cls[2 * r]     = at;
+        cls[2 * r + 1] = slot[(size_t)c] * 16;
+        for (const PairW& q : f.classes[(size_t)c]) {
             pairs[at].k16 = (uint16_t)(q.k * 16);
             pairs[at].l16 = (uint16_t)(q.l * 16);
             pairs[at].w   = (float)q.w;
@@ -858,17 +894,34 @@ extern "C" int64_t fpa_nwave_factor_table(int32_t N, const fpa_triplet* triplets
         }
         while (at & 3) pairs[at++] = FactPair{0, 0, 0.0f};     // padding: weight 0
     }
-    cls[C] = at;
+    cls[2 * C]     = at;
+    cls[2 * C + 1] = C * 16;
     for (int n = 0; n < N; ++n)
-        for (int r = 0; r < lpr; ++r)
-            for (int i = 0; i < cpl4; ++i) {
-                const int m = r + lpr * i;
-                const int c = m < N ? f.cmap[(size_t)n * N + m] : -1;
-                cmap[((size_t)n * lpr + r) * cpl4 + i] = (uint32_t)(c < 0 ? C : rank[(size_t)c]) * 16u;
-            }
+        for (int q = 0; q < n_pad; ++q) {
+            int m = 0;      // bit reversal of q over np_log bits
+            for (int bit = 0; bit < np_log; ++bit) m |= ((q >> bit) & 1) << (np_log - 1 - bit);
+            const int c = m < N ? f.cmap[(size_t)n * N + m] : -1;
+            cmap[(size_t)n * n_pad + q] = (uint32_t)(c < 0 ? C : slot[(size_t)c]) * 16u;
+        }
     if (f.mode == 1)
         for (size_t i = 0; i < (size_t)N * N; ++i) wown[i] = (int16_t)f.wown[i];
     return h.bytes;
+}
+
+extern "C" double fpa_nwave_factored_flops_per_step(const void* blob) {
+    // per RHS: 8 per non-empty cell (T * conj(At_m), accumulated), 10 per pair product (complex product 6, weighted
+    // accumulate 4), c*N as for the entry list (c = 30); per step 4 RHS + 26*N
+    if (blob == nullptr) return 0.0;
+    const unsigned char*   base = static_cast<const unsigned char*>(blob);
+    const fpa::FactHeader* h = reinterpret_cast<const fpa::FactHeader*>(base);
+    if (h->magic != fpa::kFactMagic) return 0.0;
+    const fpa::FactPair* pairs = reinterpret_cast<const fpa::FactPair*>(base + h->off_pairs);
+    const uint32_t*      cmap = reinterpret_cast<const uint32_t*>(base + h->off_cmap);
+    int64_t              live = 0, cells = 0;
+    for (int32_t e = 0; e < h->n_pairs; ++e) live += pairs[e].w != 0.0f;
+    for (int64_t i = 0; i < ((int64_t)h->n_waves << h->np_log); ++i) cells += cmap[i] != (uint32_t)h->n_classes * 16u;
+    const double rhs = 8.0 * (double)cells + 10.0 * (double)live + 30.0 * (double)h->n_waves;
+    return 4.0 * rhs + 26.0 * (double)h->n_waves;
 }
 
 extern "C" double fpa_nwave_flops_per_step(int32_t n_waves, int64_t n_triplets, int64_t n_pairs) {

@@ -50,9 +50,13 @@ class NWavePlan:
         return int(self.grid_index.max() - self.grid_index.min() + 1)
 
     def flops_per_step(self, form: str = "table") -> float:
-        """Algorithmic flops per point.step credited to the kernel that runs (`table` | `comb`)."""
+        """Algorithmic flops per point.step credited to the kernel that runs: `comb`, `table` (the table kernel on
+        the factored table), `entries` (the table kernel walking the entry list)."""
         if form == "comb":
             return float(_lib.lib().fpa_nwave_comb_flops_per_step(self.n_waves, self.grid_span))
+        if form == "table":
+            blob, _ = _device.factor_table(self.n_waves, self.table, self.row_ptr)
+            return float(_lib.lib().fpa_nwave_factored_flops_per_step(_device.ptr(blob)))
         return float(_lib.lib().fpa_nwave_flops_per_step(self.n_waves, self.n_triplets, self.n_pairs()))
 
 

@@ -92,35 +92,37 @@ def test_off_grid_triplet_enumerator_bit_exact(fpa, nw_oracle):
 
 
 def _decode_factored(blob):
-    """The blob of `fpa_nwave_factor_table` (csrc/nwave.cu, FactHeader): class offsets, pair records
-    {k*16, l*16, float weight} padded to multiples of four per class, the cell map in lane order (byte offsets
-    into the class sums, empty cells -> slot n_classes), the own-pair weights (mode 1) -> plain arrays."""
+    """The blob of `fpa_nwave_factor_table` (csrc/nwave.cu, FactHeader): per class {first pair, slot byte offset},
+    pair records {k*16, l*16, float weight} padded to multiples of four per class, the cell map (byte offsets into
+    the class sums, empty / padding cells -> slot n_classes) in bit-reversed order of m over N_pad = 2^np_log,
+    the own-pair weights (mode 1) -> plain arrays."""
     h = np.frombuffer(blob[:48], dtype=np.int32)
-    assert int(h[0]) == 0x32504146
-    N, nc, n_pairs, mode, lpr_log, cpl4, o_cls, o_pairs, o_cmap, o_wown, nbytes = (int(v) for v in h[1:12])
+    assert int(h[0]) == 0x33504146
+    N, nc, n_pairs, mode, np_log, _, o_cls, o_pairs, o_cmap, o_wown, nbytes = (int(v) for v in h[1:12])
     assert nbytes == blob.size
-    lpr = 1 << lpr_log
-    assert lpr == max(1, min(32, 1 << int(np.floor(np.log2(256 / N))))) and cpl4 % 4 == 0 and cpl4 * lpr >= N
-    cls = np.frombuffer(blob[o_cls:o_cls + 4 * (nc + 1)], dtype=np.int32)
+    n_pad = 1 << np_log
+    assert n_pad >= N and (n_pad == 1 or n_pad // 2 < N)
+    cls2 = np.frombuffer(blob[o_cls:o_cls + 8 * (nc + 1)], dtype=np.int32).reshape(nc + 1, 2)
+    cls, slot = cls2[:, 0], cls2[:nc, 1] // 16
     rec = np.frombuffer(blob[o_pairs:o_pairs + 8 * n_pairs], dtype=np.dtype([("k16", "<u2"), ("l16", "<u2"), ("w", "<f4")]))
-    lane = np.frombuffer(blob[o_cmap:o_cmap + 4 * N * lpr * cpl4], dtype=np.uint32).reshape(N, lpr, cpl4)
+    rev = np.frombuffer(blob[o_cmap:o_cmap + 4 * N * n_pad], dtype=np.uint32).reshape(N, n_pad)
     assert cls[0] == 0 and cls[-1] == n_pairs and np.all(np.diff(cls) >= 0) and np.all(np.diff(cls) % 4 == 0)
-    assert np.all(lane % 16 == 0) and np.all(rec["k16"] % 16 == 0) and np.all(rec["l16"] % 16 == 0)
+    assert sorted(slot.tolist()) == list(range(nc))                 # every class sum has a slot of its own
+    assert np.all(rev % 16 == 0) and np.all(rec["k16"] % 16 == 0) and np.all(rec["l16"] % 16 == 0)
     cmap = np.full((N, N), nc, dtype=np.int64)
-    for r in range(lpr):
-        for i in range(cpl4):
-            m = r + lpr * i
-            if m < N:
-                cmap[:, m] = lane[:, r, i] // 16
-            else:
-                assert np.all(lane[:, r, i] == 16 * nc)        # padding cells point at the zero slot
+    for q in range(n_pad):
+        m = int(format(q, f"0{np_log}b")[::-1], 2) if np_log else 0
+        if m < N:
+            cmap[:, m] = rev[:, q] // 16
+        else:
+            assert np.all(rev[:, q] == 16 * nc)                     # padding cells point at the zero slot
     if mode == 1:
         wown = np.frombuffer(blob[o_wown:o_wown + 2 * N * N], dtype=np.int16).reshape(N, N).astype(float)
     elif mode == 2:
         wown = 2.0 - np.eye(N)
     else:
         wown = np.zeros((N, N))
-    return N, nc, cls, rec, cmap, wown, mode
+    return N, nc, cls, rec, cmap, wown, mode, slot
 
 
 def _sum_entry_list(table, rows, A):
@@ -132,9 +134,11 @@ def _sum_entry_list(table, rows, A):
 
 
 def _sum_factored(blob, A):
-    N, nc, cls, rec, cmap, wown, _ = _decode_factored(blob)
+    N, nc, cls, rec, cmap, wown, _, slot = _decode_factored(blob)
     prod = rec["w"].astype(float) * A[rec["k16"] // 16] * A[rec["l16"] // 16]
-    T = np.array([prod[cls[c]:cls[c + 1]].sum() for c in range(nc)] + [0.0])
+    T = np.zeros(nc + 1, dtype=complex)
+    for c in range(nc):
+        T[slot[c]] = prod[cls[c]:cls[c + 1]].sum()
     return (T[cmap] * np.conj(A)[None, :]).sum(axis=1) - A * (wown * np.abs(A)[None, :] ** 2).sum(axis=1)
 
 
@@ -169,7 +173,7 @@ def test_factored_table_is_the_same_sum(fpa, case):
         table = np.empty(0, dtype=fpa._lib.TRIPLET_DTYPE)
         rows = np.zeros(N + 1, dtype=np.int64)
     blob, nc = dev.factor_table(N, table, rows)
-    dN, dnc, cls, pairs, cmap, wown, mode = _decode_factored(blob)
+    dN, dnc, cls, pairs, cmap, wown, mode, slot = _decode_factored(blob)
     assert (dN, dnc) == (N, nc)
     A = rng.normal(size=N) + 1j * rng.normal(size=N)
     want, got = _sum_entry_list(table, rows, A), _sum_factored(blob, A)
@@ -180,6 +184,11 @@ def test_factored_table_is_the_same_sum(fpa, case):
         # cell, so the correction is (2S - P_n) At_n and needs no matrix
         assert mode == 2 and nc == 2 * N - 1 and live == N * (N + 1) // 2 and table.size == 84320
         assert np.all(np.diff(np.diff(cls)) <= 0)      # classes of similar size next to each other
+        assert np.array_equal(cmap, np.add.outer(np.arange(N), np.arange(N)))   # slots in order of the sum frequency
+        # credited per step: 4 RHS x (8 per cell, 10 per pair product, 30 N) + 26 N
+        want_flops = 4 * (8 * N * N + 10 * (N * (N + 1) // 2) + 30 * N) + 26 * N
+        assert fpa._lib.lib().fpa_nwave_factored_flops_per_step(dev.ptr(blob)) == want_flops == 223616
+        assert fpa._lib.lib().fpa_nwave_factored_flops_per_step(dev.ptr(np.zeros(64, dtype=np.uint8))) == 0.0
     if case == "fixed4":        # the reference's four-process table: two pair products, nothing added
         assert mode == 0 and nc == 2 and live == 2
     if case == "empty":

@@ -98,7 +98,7 @@ def test_n64_comb_batch_vs_oracle(gpu, nw_oracle):
             # of the sum they are a small difference of (|A_pump|^3 * gamma * z)
             strong = np.abs(A_ref[-1]) ** 2 > 1e-9
             assert rel_err(np.abs(r["A_end"][b][strong]) ** 2, np.abs(A_ref[-1][strong]) ** 2) < 1e-10, form
-    assert plan.flops_per_step("comb") < plan.flops_per_step("table") / 10
+    assert plan.flops_per_step("comb") < plan.flops_per_step("entries") / 10
     # per-point gamma: a batch equals the single runs, bit for bit
     g = np.array([5e-3, 11.5e-3, 2e-2])
     rb = nw.run_nwave_simulation(cfg, plan, gamma=g, alpha=2e-4, A0=A0, beta=beta, outputs=("end",))
