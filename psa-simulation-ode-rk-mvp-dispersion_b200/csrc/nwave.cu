@@ -81,7 +81,6 @@ struct FactPair {
 };
 constexpr uint32_t kFactMagic   = 0x33504146u;   // "FAP3"
 constexpr int      kFactMaxCls  = 1 << 20;
-constexpr int      kFactThreads = 256;           // per point; 512 when the batch leaves SMs to spare
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -202,10 +201,10 @@ __device__ double rhs_stage(const Smem& s, const NwaveParams& p, const fpa_tripl
 }
 
 #ifdef FPA_FACT_TIMING   // tools/fact_phase_timing.py: thread 0 of point 0 accumulates clock64() between the phases
-__device__ long long g_fact_ticks[8];
+__shared__ long long g_fact_ticks[12];
 #define FPA_FTICK(k)                                        \
     do {                                                    \
-        if (blockIdx.x == 0 && threadIdx.x == 0) {          \
+        if (threadIdx.x == 0) {                             \
             const long long t_now = clock64();              \
             g_fact_ticks[k] += t_now - t_last;              \
             t_last = t_now;                                 \
@@ -237,7 +236,9 @@ __device__ __forceinline__ FactView fact_view(const NwaveParams& p) {
     // lanes per row: as many as the CTA has for N_pad rows, at least four cells per lane (one 16-byte load)
     const int t_log = 31 - __clz((int)blockDim.x);
     f.lpr_log = max(0, min(min(5, f.np_log - 2), t_log - f.np_log));
-    // lanes per class: 4, more when the CTA has lanes to spare for all classes at once
+    // lanes per class: 4, more when the CTA has lanes to spare for all classes at once (8 lanes per class make the
+    // operand loads of a quarter-warp conflict-free -- one class, neighbouring words -- but cost a shuffle level and
+    // a second pass over the classes: measured 6 % slower at N = 64)
     f.lpc_log = 2;
     while (f.lpc_log < 5 && (f.C << (f.lpc_log + 1)) <= (int)blockDim.x) ++f.lpc_log;
     return f;
@@ -253,7 +254,12 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
     const unsigned char* Atb = reinterpret_cast<const unsigned char*>(s.At);
     const unsigned char* Tb  = reinterpret_cast<const unsigned char*>(s.T);
 #ifdef FPA_FACT_TIMING
-    long long t_last = clock64();
+    long long t_last = clock64(), t_sub = 0;
+#define FPA_FSUB0() do { if (threadIdx.x == 0) t_sub = clock64(); } while (0)
+#define FPA_FSUB(k, dep) do { if (threadIdx.x == 0 && (dep) == (dep)) { const long long t_n = clock64(); g_fact_ticks[k] += t_n - t_sub; t_sub = t_n; } } while (0)
+#else
+#define FPA_FSUB0()
+#define FPA_FSUB(k, dep)
 #endif
 
     double part = 0.0;
@@ -274,12 +280,13 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
     if (lane == 0) s.red[warp] = part;
     __syncthreads();
     FPA_FTICK(1);
-    double S = 0.0, S1 = 0.0;
-    for (int w = 0; w + 1 < nwarps; w += 2) {
+    const int nw_sum = min(nwarps, (N + 31) >> 5);      // the warps that had waves to rotate
+    double    S = 0.0, S1 = 0.0;
+    for (int w = 0; w + 1 < nw_sum; w += 2) {
         S += s.red[w];
         S1 += s.red[w + 1];
     }
-    if (nwarps & 1) S += s.red[nwarps - 1];
+    if (nw_sum & 1) S += s.red[nw_sum - 1];
     S += S1;
 
     // class sums T_c: lpc lanes per class, two pairs of a lane in flight
@@ -297,6 +304,7 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
         const int c = base + (tid >> lpc_log);
         double    qr = 0.0, qi = 0.0, q2 = 0.0, j2 = 0.0;
         int       slot = 0;
+        FPA_FSUB0();
         if (c < f.C) {
             const uint2* pp = reinterpret_cast<const uint2*>(f.pairs);
             const int2   c0 = __ldg(f.cls + c);
@@ -312,11 +320,14 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
             qr += q2;
             qi += j2;
         }
+        FPA_FSUB(6, qr + qi);
         for (int o = lpc >> 1; o > 0; o >>= 1) {
             qr += __shfl_xor_sync(0xffffffffu, qr, o);
             qi += __shfl_xor_sync(0xffffffffu, qi, o);
         }
+        FPA_FSUB(7, qr + qi);
         if (c < f.C && csub == 0) *reinterpret_cast<double2*>(const_cast<unsigned char*>(Tb) + slot) = make_double2(qr, qi);
+        FPA_FSUB(8, 0.0);
     }
     FPA_FTICK(2);
     __syncthreads();
@@ -330,6 +341,7 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
     for (int base = 0; base < N; base += (int)(blockDim.x >> lpr_log)) {
         const int n = base + (tid >> lpr_log);
         double    rr = 0.0, ri = 0.0, r2 = 0.0, i2 = 0.0, r3 = 0.0, i3 = 0.0, r4 = 0.0, i4 = 0.0, cw = 0.0;
+        FPA_FSUB0();
         if (n < N) {
             const int    q0 = rsub * cpl;
             const uint4* cm = reinterpret_cast<const uint4*>(f.cmap + ((size_t)n << f.np_log) + q0);
@@ -369,11 +381,13 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
                 for (int m = rsub; m < N; m += lpr) cw = fma((double)__ldg(wo + m), s.P[m], cw);
             }
         }
+        FPA_FSUB(9, rr + ri);
         for (int o = lpr >> 1; o > 0; o >>= 1) {
             rr += __shfl_xor_sync(0xffffffffu, rr, o);
             ri += __shfl_xor_sync(0xffffffffu, ri, o);
             if (f.mode == 1) cw += __shfl_xor_sync(0xffffffffu, cw, o);
         }
+        FPA_FSUB(10, rr + ri);
         if (n < N && rsub == 0) {
             const double xr = s.ys[2 * n], xi = s.ys[2 * n + 1];
             const double er = s.E[2 * n], ei = s.E[2 * n + 1];
@@ -397,6 +411,7 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
                 s.ys[2 * n + 1] = fma(wb, ki, bq);
             }
         }
+        FPA_FSUB(11, 0.0);
     }
     FPA_FTICK(4);
     __syncthreads();
@@ -427,6 +442,9 @@ __global__ void __launch_bounds__(1024) nwave_rk4_kernel(const NwaveParams p) {
     if (FACT) {
         fv = fact_view(p);
         if (fv.ok && tid == 0) s.T[fv.C] = make_double2(0.0, 0.0);   // the slot empty cells point at
+#ifdef FPA_FACT_TIMING
+        if (tid < 12) g_fact_ticks[tid] = 0;
+#endif
     } else {
         for (int j = tid; j <= N; j += blockDim.x) s.rows[j] = (int)p.row_ptr[j];
         if (p.table_in_smem) {
@@ -524,10 +542,11 @@ __global__ void __launch_bounds__(1024) nwave_rk4_kernel(const NwaveParams p) {
 #ifdef FPA_FACT_TIMING
     if (FACT && b == 0 && tid == 0) {
         const double per = 1.0 / (4.0 * n_steps);
-        printf("fact stage cycles (thread 0 of point 0, per stage): phases %.0f | sum+sync %.0f | classes %.0f | sync %.0f | rows %.0f | sync %.0f\n",
+        printf("fact stage cycles (thread 0 of point 0, per stage): phases %.0f | sum+sync %.0f | classes %.0f | sync %.0f | rows %.0f | sync %.0f"
+               " || classes: loads+products %.0f, shuffles %.0f, store %.0f || rows: cells %.0f, shuffles %.0f, owner %.0f\n",
                g_fact_ticks[0] * per, g_fact_ticks[1] * per, g_fact_ticks[2] * per, g_fact_ticks[3] * per,
-               g_fact_ticks[4] * per, g_fact_ticks[5] * per);
-        for (int k = 0; k < 8; ++k) g_fact_ticks[k] = 0;
+               g_fact_ticks[4] * per, g_fact_ticks[5] * per, g_fact_ticks[6] * per, g_fact_ticks[7] * per,
+               g_fact_ticks[8] * per, g_fact_ticks[9] * per, g_fact_ticks[10] * per, g_fact_ticks[11] * per);
     }
 #endif
     if (p.A_end)
@@ -609,14 +628,19 @@ int nwave_launch(const fpa_nwave_desc* d, cudaStream_t st) {
         // state + class sums: 8.4 KB for N = 64 -- one CTA of 256 threads per point, several per SM
         const size_t smem = nwave_smem_bytes(d->n_waves, 0) + (size_t)(p.n_classes + 1) * sizeof(double2);
         if (smem <= 200 * 1024) {
-            // a batch that leaves SMs to spare gets 512 threads per point (a single run is one CTA whatever its size:
-            // the latencies of its passes are all there is to hide; 1024 threads cost more in instructions issued
-            // by lanes without work than they hide); FPA_FACT_THREADS overrides (tools)
+            // threads per point (profiles/r2_fact_thread_sweep.txt): about 1 024 per SM in all -- 64 (128 above 64
+            // waves) for large batches: many small CTAs per SM hide each other's barriers and load latencies best --
+            // up to 512 when the batch leaves SMs to spare: a single run is one CTA whatever its size, the latencies
+            // of its own passes are all there is to hide (1 024 threads cost more in instructions issued by lanes
+            // without work than they hide).  FPA_FACT_THREADS overrides (tools)
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             const int env_threads = getenv("FPA_FACT_THREADS") ? atoi(getenv("FPA_FACT_THREADS")) : 0;
-            int       threads = d->n_points <= 2 * (int64_t)sms ? 512 : kFactThreads;
+            const int     lo = d->n_waves <= 64 ? 64 : 128, hi = d->n_waves <= 12 ? 64 : (d->n_waves <= 32 ? 256 : 512);
+            const int64_t per_sm = (d->n_points + sms - 1) / sms;      // points an SM gets at once
+            int           threads = hi;
+            while (threads > lo && threads * per_sm > 1024) threads >>= 1;
             if (env_threads >= 32 && env_threads <= 1024) threads = env_threads & ~31;
             cudaError_t      e = cudaFuncSetAttribute(nwave_rk4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(nwave_rk4_kernel<factored>)");
