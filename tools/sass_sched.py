@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import argparse
 import random
+import os
 import re
 import struct
 import subprocess
@@ -387,9 +388,13 @@ def build_deps(seq):
                     elif j != w:
                         add(w, j, 1)
                         add(i, w, 2)
-    # a wait on a barrier that was set before the block: everything behind it that touches
-    # values from outside the block stays behind it
-    set_in_block = set()
+    # The FIRST wait of the block on a barrier may be the wait for an instruction issued before the block (in a
+    # loop: by the previous iteration) -- also when the block itself has set that barrier again before the wait
+    # (the scoreboards are counters: one wait covers both).  Everything behind such a wait that touches values
+    # from outside the block stays behind it.  (Until round 2 this rule skipped barriers already set in the block:
+    # the comb kernel's bodies, which re-use a barrier for the next window load before they wait for the previous
+    # one, were then re-ordered so that a consumer of the OLD load ran ahead of its wait -- wrong results.)
+    waited = set()
     defined = set()
     live_in_user = []
     for j, x in enumerate(seq):
@@ -397,13 +402,11 @@ def build_deps(seq):
         defined |= x.defs
     for j, x in enumerate(seq):
         for b in range(6):
-            if (x.get("wait") >> b) & 1 and b not in set_in_block:
+            if (x.get("wait") >> b) & 1 and b not in waited:
+                waited.add(b)
                 for k in range(j + 1, n):
                     if live_in_user[k]:
                         add(j, k, 1)
-        for bar in (x.get("wb"), x.get("rb")):
-            if bar != 7:
-                set_in_block.add(bar)
     # the block's last instruction stays last when it is a control instruction
     if seq[-1].base in CONTROL:
         for i in range(n - 1):
@@ -917,9 +920,14 @@ def patch_function(ins, mode, tries, log, stall_cost=0.05, w_over=None, kept=Non
                 # hot blocks, whose only variable-latency instructions are constant-bank loads, I2F and MUFU of the
                 # phase re-synchronisation.  The N-wave comb kernel's blocks refill their rolling register windows
                 # from shared memory in the middle of the arithmetic that still reads them; re-ordered, they passed
-                # the symbolic check and computed DIFFERENT values on the GPU (round-2 experiment).
-                if any(x_.base in ("LDS", "LDG", "LDL", "LD", "LDSM") for x_ in seq):
+                # the symbolic check and computed DIFFERENT values on the GPU (round-2 experiments, the second one
+                # after the first-wait rule of build_deps had closed one such hazard: still different, and no faster
+                # than the flags-only mode).  FPA_SASS_ALLOW_LOADS=1 lifts the envelope for experiments.
+                if any(x_.base in ("LDS", "LDG", "LDL", "LD", "LDSM") for x_ in seq) and not os.environ.get("FPA_SASS_ALLOW_LOADS"):
                     raise ValueError("block holds memory loads: outside the validated envelope of the pass")
+                only = os.environ.get("FPA_SASS_ONLY_BLOCK")        # experiments: re-order one hot block only
+                if only is not None and blocks.index(b) != int(only):
+                    raise ValueError("experiment: not the selected block")
                 new, st = schedule_block(seq, tries=tries, stall_cost=stall_cost, w_over=w_over, beam_width=48)
                 verify_block(seq, new)
             except (ValueError, SassVerifyError) as e:  # keep ptxas' block rather than risk it
