@@ -36,6 +36,30 @@ def test_struct_layouts_match_header(fpa):
     assert C.sizeof(L.Triplet) == 8 and L.TRIPLET_DTYPE.itemsize == 8
 
 
+def test_struct_layouts_match_the_compiled_header(fpa, tmp_path):
+    """The same check done by the C compiler: sizeof and the offsets of the last fields of every descriptor of
+    include/fpa_b200.h against the ctypes mirrors of _lib.py."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    L = fpa._lib
+    cases = {"fpa_yaman4_desc": (L.Yaman4Desc, "scratch"), "fpa_plan_desc": (L.PlanDesc, "valid"),
+             "fpa_sweep_desc": (L.SweepDesc, "peer_gain"), "fpa_nwave_desc": (L.NwaveDesc, "factored"),
+             "fpa_triplet": (L.Triplet, "weight")}
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "fpa_b200.h"\nint main(void) {\n'
+    for name, (_, field) in cases.items():
+        prog += f'  printf("{name} %zu %zu\\n", sizeof({name}), offsetof({name}, {field}));\n'
+    prog += "  return 0;\n}\n"
+    src, exe = tmp_path / "sizes.c", tmp_path / "sizes"
+    src.write_text(prog)
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    got = {out[i]: (int(out[i + 1]), int(out[i + 2])) for i in range(0, len(out), 3)}
+    for name, (ct, field) in cases.items():
+        assert got[name] == (C.sizeof(ct), getattr(ct, field).offset), name
+
+
 def test_host_helpers(fpa):
     h = fpa._lib.lib()
     assert h.fpa_n_saved(10000, 10) == 1001 and h.fpa_n_saved(10, 3) == 4 and h.fpa_n_saved(5, 7) == 1
