@@ -166,7 +166,18 @@ def _sum_factored(blob, A):
     return (T[cmap] * np.conj(A)[None, :]).sum(axis=1) - A * (wown * np.abs(A)[None, :] ** 2).sum(axis=1)
 
 
-@pytest.mark.parametrize("case", ["comb64", "gapped", "offgrid", "fixed4", "ragged", "empty"])
+def comb_table_with_an_own_pair(fpa, N=16):
+    """A comb's table plus ONE entry whose pair is the cell's own {n, m} (n = 0: k = 0, l = 1, m = 1) -- the
+    factoriser then cannot put the own pair into every cell and keeps the weight matrix (mode 1)."""
+    table, rows = fpa._device.enumerate_triplets(np.arange(N))
+    extra = np.array([(0, 1, 1, 3)], dtype=fpa._lib.TRIPLET_DTYPE)
+    table = np.concatenate((table[:rows[1]], extra, table[rows[1]:]))
+    rows = rows.copy()
+    rows[1:] += 1
+    return table, rows
+
+
+@pytest.mark.parametrize("case", ["comb64", "gapped", "offgrid", "fixed4", "ragged", "ownpair", "empty"])
 def test_factored_table_is_the_same_sum(fpa, case):
     """`fpa_nwave_factor_table`: whatever the table, the factored form sums to the entry list's triplet sums."""
     dev = fpa._device
@@ -187,6 +198,9 @@ def test_factored_table_is_the_same_sum(fpa, case):
         N = 4
         table = np.array([(2, 3, 1, 2), (2, 3, 0, 2), (0, 1, 3, 2), (0, 1, 2, 2)], dtype=fpa._lib.TRIPLET_DTYPE)
         rows = np.arange(5, dtype=np.int64)
+    elif case == "ownpair":
+        N = 16
+        table, rows = comb_table_with_an_own_pair(fpa, N)
     elif case == "ragged":      # nothing a frequency plan would give: repeats, k > l, odd weights, empty rows
         N = 7
         ent = [(0, 3, 2, 1, 5), (0, 2, 3, 1, -2), (0, 1, 1, 0, 3), (0, 6, 6, 0, 1), (2, 5, 4, 2, 7), (2, 0, 1, 3, 1), (6, 0, 0, 0, 1)]
@@ -213,6 +227,8 @@ def test_factored_table_is_the_same_sum(fpa, case):
         want_flops = 4 * (8 * N * N + 10 * (N * (N + 1) // 2) + 30 * N) + 26 * N
         assert fpa._lib.lib().fpa_nwave_factored_flops_per_step(dev.ptr(blob)) == want_flops == 223616
         assert fpa._lib.lib().fpa_nwave_factored_flops_per_step(dev.ptr(np.zeros(64, dtype=np.uint8))) == 0.0
+    if case == "ownpair":       # own pairs where a group has entries, taken out again through the weight matrix
+        assert mode == 1 and wown[0, 1] == 0 and wown[1, 0] == 0 and wown[2, 5] == 2 and wown[5, 5] == 1
     if case == "fixed4":        # the reference's four-process table: two pair products, nothing added
         assert mode == 0 and nc == 2 and live == 2
     if case == "empty":

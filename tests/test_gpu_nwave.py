@@ -134,7 +134,7 @@ def test_nwave_invariants(gpu):
 
 
 @pytest.mark.parametrize("lines", [[0], [0, 1], list(range(-3, 4)), list(range(-16, 17)), [0, 1, 2, 100],
-                                   list(range(-40, 41)), list(range(0, 127, 2))])
+                                   list(range(-40, 41)), list(range(0, 127, 2)), list(range(-64, 64))])
 @pytest.mark.parametrize("batch", [2, 640])          # CTA-per-point and warp-per-point mappings
 def test_comb_equals_table_on_odd_shapes(gpu, lines, batch):
     """Grid spans that are not multiples of the kernel's tile (2, 4) or block (8) sizes, one and two
@@ -178,7 +178,12 @@ def test_factored_table_equals_entry_list(gpu, nw_oracle):
     ent = [(0, 3, 2, 1, 5), (0, 2, 3, 1, -2), (0, 1, 1, 0, 3), (0, 6, 6, 0, 1), (2, 5, 4, 2, 7), (2, 0, 1, 3, 1), (6, 0, 0, 0, 1)]
     ragged = np.array([e[1:] for e in ent], dtype=gpu._lib.TRIPLET_DTYPE)
     rrows = np.searchsorted(np.array([e[0] for e in ent]), np.arange(8)).astype(np.int64)
-    cases.append((7, ragged, rrows, rng.uniform(-2.0, 2.0, 7)))
+    ragged_case = (7, ragged, rrows, rng.uniform(-2.0, 2.0, 7))
+    cases.append(ragged_case)
+    from test_cabi_cpu import comb_table_with_an_own_pair      # mode 1 of the factoriser: own-pair weight matrix
+    own_t, own_r = comb_table_with_an_own_pair(gpu, 16)
+    assert np.frombuffer(D.factor_table(16, own_t, own_r)[0][:48], dtype=np.int32)[4] == 1
+    cases.append((16, own_t, own_r, rng.uniform(-0.5, 0.5, 16)))
     for N, table, rows, beta in cases:
         B = 3
         A0 = np.sqrt(rng.uniform(1e-4, 0.3, (B, N))) * np.exp(1j * rng.uniform(0, 6.28, (B, N)))
@@ -190,7 +195,7 @@ def test_factored_table_equals_entry_list(gpu, nw_oracle):
         for key, pw in (("A_trace", 1), ("A_end", 1), ("Pmax", 2)):
             assert np.max(np.abs(f[key] - e[key])) < 1e-13 * scale ** pw, (N, key)
     # the ragged table against the CPU march
-    N, table, rows, beta = cases[-1]
+    N, table, rows, beta = ragged_case
     A0 = np.sqrt(rng.uniform(1e-4, 0.3, N)) * np.exp(1j * rng.uniform(0, 6.28, N))
     f = D.nwave_batch(beta, 0.02, 1e-4, A0[None, :], table, rows, z_max=6.0, n_steps=60, save_every=6, trace=True, force_table=True)
     tl = [(int(a), int(b), int(c), int(d)) for a, b, c, d in zip(table["k"], table["l"], table["m"], table["weight"])]
