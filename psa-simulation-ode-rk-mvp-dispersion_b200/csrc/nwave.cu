@@ -24,6 +24,15 @@
 #include <map>
 #include <vector>
 
+// compute-sanitizer is not available on the B200 pool: -DFPA_BOUNDS_CHECK checks every index the factored-table
+// kernel takes from its blob (device assert); tools/bounds_check.py builds that variant and runs the shapes.
+#ifdef FPA_BOUNDS_CHECK
+#include <assert.h>
+#define FPA_IN_RANGE(idx, n) assert((long long)(idx) >= 0 && (long long)(idx) < (long long)(n))
+#else
+#define FPA_IN_RANGE(idx, n) ((void)0)
+#endif
+
 namespace fpa {
 
 struct NwaveParams {
@@ -292,6 +301,8 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
     // class sums T_c: lpc lanes per class, two pairs of a lane in flight
     const int lpc_log = f.lpc_log, lpc = 1 << lpc_log, csub = tid & (lpc - 1);
     auto      pair_term = [&](const uint2 u, double& qr, double& qi) {
+        FPA_IN_RANGE(u.x & 0xFFFFu, 16 * N);
+        FPA_IN_RANGE(u.x >> 16, 16 * N);
         const double2 a = *reinterpret_cast<const double2*>(Atb + (u.x & 0xFFFFu));
         const double2 b = *reinterpret_cast<const double2*>(Atb + (u.x >> 16));
         const double  w = (double)__uint_as_float(u.y);
@@ -311,6 +322,8 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
             const int    e1 = __ldg(f.cls + c + 1).x;
             int          e = c0.x + csub;
             slot           = c0.y;
+            FPA_IN_RANGE(slot, 16 * f.C);
+            FPA_IN_RANGE(c0.x, e1 + 1);
             for (; e + lpc < e1; e += 2 * lpc) {
                 const uint2 u0 = __ldg(pp + e), u1 = __ldg(pp + e + lpc);
                 pair_term(u0, qr, qi);
@@ -350,6 +363,11 @@ __device__ double fact_stage(const Smem& s, const NwaveParams& p, const FactView
                 uint4 o = __ldg(cm);
                 for (int i = 0; i < cpl; i += 4) {
                     const uint4   on = __ldg(cm + (i + 4 < cpl ? (i >> 2) + 1 : 0));
+                    FPA_IN_RANGE(o.x, 16 * (f.C + 1));
+                    FPA_IN_RANGE(o.y, 16 * (f.C + 1));
+                    FPA_IN_RANGE(o.z, 16 * (f.C + 1));
+                    FPA_IN_RANGE(o.w, 16 * (f.C + 1));
+                    FPA_IN_RANGE(q0 + i + 3, 1 << f.np_log);
                     const double2 t0 = *reinterpret_cast<const double2*>(Tb + o.x);
                     const double2 t1 = *reinterpret_cast<const double2*>(Tb + o.y);
                     const double2 t2 = *reinterpret_cast<const double2*>(Tb + o.z);
