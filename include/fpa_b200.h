@@ -327,7 +327,9 @@ typedef struct fpa_nwave_desc {
 /* Factor a CSR triplet table (host pointers) into the blob `factored` points to.  Returns the blob size in bytes
  * (and the class count in *n_classes); the blob is written when `blob` is not NULL and `cap` is large enough.
  * Any table factors -- nothing is assumed about where it came from; -1 on malformed input (N > 128, indices out
- * of range, row_ptr not a CSR offset array). */
+ * of range, row_ptr not a CSR offset array).  The size query and the fill call of one plan cost one
+ * factorisation (11 ms at N = 64): the library keeps the calling thread's last result, keyed by a hash of the
+ * table, which also serves the host integrator calls that repeat a plan. */
 int64_t fpa_nwave_factor_table(int32_t N, const fpa_triplet* triplets, const int64_t* row_ptr, int64_t n_triplets,
                                void* blob, int64_t cap, int32_t* n_classes);
 

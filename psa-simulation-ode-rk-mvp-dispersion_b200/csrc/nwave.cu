@@ -824,8 +824,9 @@ bool factor_groups(int N, const std::vector<std::vector<PairW>>& groups, int mod
 }
 }  // namespace
 
-extern "C" int64_t fpa_nwave_factor_table(int32_t N, const fpa_triplet* triplets, const int64_t* row_ptr, int64_t n_triplets,
-                                          void* blob, int64_t cap, int32_t* n_classes) {
+// Factor the table into *out (resized).  Returns the blob size or -1.
+static int64_t factor_build(int32_t N, const fpa_triplet* triplets, const int64_t* row_ptr, int64_t n_triplets,
+                            std::vector<unsigned char>* out, int32_t* n_classes) {
     using fpa::FactHeader;
     using fpa::FactPair;
     if (N < 1 || N > 128 || row_ptr == nullptr || n_triplets < 0 || (n_triplets > 0 && triplets == nullptr)) {
@@ -914,10 +915,8 @@ extern "C" int64_t fpa_nwave_factor_table(int32_t N, const fpa_triplet* triplets
     h.off_wown   = (int32_t)up16(h.off_cmap + (int64_t)N * n_pad * 4);
     h.bytes      = (int32_t)up16(h.off_wown + (f.mode == 1 ? (int64_t)N * N * 2 : 0));
     if (n_classes) *n_classes = C;
-    if (blob == nullptr || cap < h.bytes) return h.bytes;
-
-    unsigned char* base = static_cast<unsigned char*>(blob);
-    memset(base, 0, (size_t)h.bytes);
+    out->assign((size_t)h.bytes, 0);
+    unsigned char* base = out->data();
     memcpy(base, &h, sizeof h);
     int32_t*  cls   = reinterpret_cast<int32_t*>(base + h.off_cls);      // {first pair, slot byte offset} per class
     FactPair* pairs = reinterpret_cast<FactPair*>(base + h.off_pairs);
@@ -948,6 +947,49 @@ extern "C" int64_t fpa_nwave_factor_table(int32_t N, const fpa_triplet* triplets
     if (f.mode == 1)
         for (size_t i = 0; i < (size_t)N * N; ++i) wown[i] = (int16_t)f.wown[i];
     return h.bytes;
+}
+
+// The C entry point is called twice per plan (size, then fill) and the host integrator entry points call it on
+// every launch: the last factorisation of each thread is kept, keyed by a hash of the table.
+extern "C" int64_t fpa_nwave_factor_table(int32_t N, const fpa_triplet* triplets, const int64_t* row_ptr, int64_t n_triplets,
+                                          void* blob, int64_t cap, int32_t* n_classes) {
+    if (N < 1 || N > 128 || row_ptr == nullptr || n_triplets < 0 || (n_triplets > 0 && triplets == nullptr)) {
+        fpa::set_error("fpa_nwave_factor_table: need 1 <= N <= 128 and a CSR triplet table");
+        return -1;
+    }
+    struct Cached {
+        uint64_t                   key = 0;
+        int32_t                    N = 0, C = 0;
+        int64_t                    nt = -1;
+        std::vector<unsigned char> blob;
+    };
+    static thread_local Cached last;
+    auto fnv = [](uint64_t h, const void* data, size_t bytes) {
+        const unsigned char* p = static_cast<const unsigned char*>(data);
+        size_t               i = 0;
+        for (; i + 8 <= bytes; i += 8) {     // word at a time: the table is ~0.7 MB at N = 64
+            uint64_t w;
+            memcpy(&w, p + i, 8);
+            h = (h ^ w) * 1099511628211ull;
+        }
+        for (; i < bytes; ++i) h = (h ^ p[i]) * 1099511628211ull;
+        return h;
+    };
+    uint64_t key = fnv(14695981039346656037ull, row_ptr, (size_t)(N + 1) * sizeof(int64_t));
+    key          = fnv(key, triplets, (size_t)n_triplets * sizeof(fpa_triplet));
+    if (!(last.nt == n_triplets && last.N == N && last.key == key && !last.blob.empty())) {
+        Cached        fresh;
+        const int64_t nb = factor_build(N, triplets, row_ptr, n_triplets, &fresh.blob, &fresh.C);
+        if (nb < 0) return -1;
+        fresh.key = key;
+        fresh.N   = N;
+        fresh.nt  = n_triplets;
+        last      = std::move(fresh);
+    }
+    if (n_classes) *n_classes = last.C;
+    const int64_t bytes = (int64_t)last.blob.size();
+    if (blob != nullptr && cap >= bytes) memcpy(blob, last.blob.data(), (size_t)bytes);
+    return bytes;
 }
 
 extern "C" double fpa_nwave_factored_flops_per_step(const void* blob) {

@@ -235,6 +235,27 @@ def test_factored_table_is_the_same_sum(fpa, case):
         assert nc == 0 and pairs.size == 0 and np.all(cmap == nc) and mode == 0
 
 
+def test_factor_table_cache_follows_the_table(fpa):
+    """The library keeps the last factorisation of the calling thread (the size and the fill call of one plan, and
+    the host entry points' call per launch, then cost a hash): a changed table must not be served from it."""
+    dev = fpa._device
+    table, rows = dev.enumerate_triplets(np.arange(12))
+    a, nca = dev.factor_table(12, table, rows)
+    b, ncb = dev.factor_table(12, table.copy(), rows.copy())            # same content elsewhere in memory
+    assert a.tobytes() == b.tobytes() and nca == ncb
+    t2 = table.copy()
+    t2["weight"][3] = 5
+    c, _ = dev.factor_table(12, t2, rows)
+    assert c.tobytes() != a.tobytes()
+    want, got = _sum_entry_list(t2, rows, np.arange(1.0, 13.0) + 0.5j), _sum_factored(c, np.arange(1.0, 13.0) + 0.5j)
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    d, _ = dev.factor_table(12, table, rows)                            # and back
+    assert d.tobytes() == a.tobytes()
+    other, rows_o = dev.enumerate_triplets(np.arange(11))               # another plan size
+    e_, nce = dev.factor_table(11, other, rows_o)
+    assert np.frombuffer(e_[:48], dtype=np.int32)[1] == 11 and nce != nca
+
+
 def test_factor_table_rejects_malformed_input(fpa):
     L = fpa._lib.lib()
     nc = C.c_int32()
