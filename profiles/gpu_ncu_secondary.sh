@@ -6,7 +6,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 CASES=${@:-"seg125k comb1024 comb comb16 trace table"}
 for c in $CASES; do
-  case $c in trace) K=yaman4_fast;; comb*) K=nwave_comb;; table) K=nwave_rk4;; seg125k) K=yaman4_sweep;; esac
+  case $c in trace) K=yaman4_fast;; comb*) K=nwave_comb;; table*) K=nwave_rk4;; seg125k) K=yaman4_sweep;; esac
   if [ $c = seg125k ]; then CMD="python bench.py --steps 2 --warmup 3 --shard-of 8 --no-cpu-baseline --no-secondary"; SKIP=3
   else CMD="python tools/profile_cases.py $c"; SKIP=1; fi
   $CMD > $OUT/plain_$c.log 2>&1 &&
