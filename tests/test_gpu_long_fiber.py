@@ -106,6 +106,31 @@ def test_config5_plan_long_fiber_comb_vs_table_vs_oracle(gpu, nw_oracle):
         assert np.max(np.abs(A - A_ref)) <= 1e-11 * np.max(np.abs(A_ref))
 
 
+def test_config5_full_size_invariants(gpu):
+    """BASELINE config 5 at its FULL size -- N = 64, B = 1024 pump powers, 1e5 z-steps of 0.1 m -- through
+    size-independent properties (no CPU statement finishes this in test time): (i) lossless fiber: the total power of
+    every point is conserved (Manley-Rowe) to RK4 accuracy over the 10 km; (ii) the same point at two positions of
+    the batch gives the same bits; (iii) with loss the total power follows exp(-alpha z) (the Kerr and mixing terms
+    conserve it, so dP/dz = -alpha P whatever the lines exchange among themselves)."""
+    nw = gpu.nwave
+    n_steps = 100_000
+    plan, beta, A0 = _config5(gpu, 512, 0.1, 1.0)
+    A0 = np.concatenate((A0, A0))                       # 1 024 points: every point twice, 512 positions apart
+    cfg = gpu.config.custom_simulation_config(z_max=0.1 * n_steps, dz=0.1, save_every=10_000)
+    r = nw.run_nwave_simulation(cfg, plan, A0=A0, gamma=11.5e-3, alpha=0.0, beta=beta, outputs=("trace", "pmax"), form="comb")
+    assert r["A_trace"].shape == (1024, 11, 64) and (r["status"] == -1).all()
+    P = (np.abs(r["A_trace"]) ** 2).sum(axis=2)         # [B, saved]
+    assert np.max(np.abs(P / P[:, :1] - 1.0)) < 1e-8
+    assert r["A_trace"][:512].tobytes() == r["A_trace"][512:].tobytes()
+    assert r["Pmax"][:512].tobytes() == r["Pmax"][512:].tobytes()
+    # cascaded mixing did happen: lines that started at 1e-12 W carry power at the end
+    assert (np.abs(r["A_trace"][:, -1, :]) ** 2 > 1e-6).sum(axis=1).min() >= 8
+    lossy = nw.run_nwave_simulation(cfg, plan, A0=A0[:64], gamma=11.5e-3, alpha=2e-4, beta=beta, outputs=("trace",), form="comb")
+    Pl = (np.abs(lossy["A_trace"]) ** 2).sum(axis=2)
+    z = lossy["z"]
+    assert np.max(np.abs(Pl / (Pl[:, :1] * np.exp(-2e-4 * z)[None, :]) - 1.0)) < 1e-8
+
+
 def test_config4_full_length_sample_vs_oracle(gpu, oracle, golden):
     """BASELINE config 4 at full size -- 1000 x 1000 grid, 2 500 steps -- against the pinned 4-wave oracle on 48
     random grid points: gain to 1e-10, dbeta to 1e-12 (what bench.py also reports as parity_max_rel_err_vs_gpu)."""
