@@ -32,12 +32,12 @@ N3 = 1000
 rows = [int(v) for v in sys.argv[1:]] or [74, 76, 100, 125, 152, 250, 500, 1000]
 seg_list = [32, 64, 128, 256]
 peak_tf, _ = fpa._device.fp64_peak(iters=2048)
-print(f"{torch.cuda.get_device_name(0)}; FP64 peak (DFMA probe) {peak_tf:.2f} TFLOP/s; 2 500 steps, 568 flops per point.step")
+n_steps = int(os.environ.get("SEG_TUNE_STEPS", "2500"))      # bench.Z_MAX / bench.DZ by default
+print(f"{torch.cuda.get_device_name(0)}; FP64 peak (DFMA probe) {peak_tf:.2f} TFLOP/s; {n_steps} steps, 568 flops per point.step")
 
 odisp = bench.fiber_dispersion(O)
 disp = fpa.dispersion.DispersionParams(omega_ref=odisp.omega_ref, beta2=odisp.b[2], beta3=odisp.b[3], beta4=odisp.b[4])
 pm_cfg = fpa.phase_matching.PhaseMatchingConfig()
-n_steps = 2500
 t_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
@@ -66,7 +66,7 @@ def run(n1, env, reps=5):
     for j in range(4):
         d.A0[2 * j], d.A0[2 * j + 1] = A0[j].real, A0[j].imag
     d.p_signal, d.gamma, d.alpha = bench.P_IN[2], bench.GAMMA, bench.ALPHA
-    d.z_max, d.dz, d.length_scale, d.save_every = bench.Z_MAX, bench.DZ, 1.0, bench.SAVE_EVERY
+    d.z_max, d.dz, d.length_scale, d.save_every = bench.DZ * n_steps, bench.DZ, 1.0, bench.SAVE_EVERY
     d.flags = L.CHECK_NAN
     d.gain_lin, d.status, d.Pmax, d.A_end = t_gain.data_ptr(), t_st.data_ptr(), None, None
     st = torch.cuda.current_stream().cuda_stream
